@@ -27,6 +27,7 @@ COMMON_FLAGS = [
 # feeding the integer tile keys (depth bits, tile bounds) are bit-identical to the C oracle.
 PER_FILE_FLAGS = {
     "raster_project.cu": ["-fmad=false"],
+    "raster_isect.cu": ["-fmad=false"],
 }
 
 

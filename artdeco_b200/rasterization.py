@@ -1,0 +1,231 @@
+"""Host-side mirror of ``gsplat.rendering.rasterization`` for the exact configuration the reference uses
+(Reconstruct/scene/scene_models/h3dgsv3.py:664-680): 3DGS "classic" rasterisation, ``packed=False``,
+``absgrad=False``, SH colours, ``render_mode`` "RGB" or "RGB+D".  Same keyword names, same return triple
+``(render_colors[C,H,W,ch], render_alphas[C,H,W,1], meta)`` with ``meta['radii']`` of shape [C,N,2]
+(h3dgsv3.py:689), and a complete autograd backward (means, quats, scales, opacities, colours, viewmats;
+upstream grads for colours AND alphas, h3dgsv3.py:685-686).
+
+All compute goes through the C ABI (adb_raster_*); PyTorch only owns memory, streams and the autograd graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import f32, i32, i64, vp
+
+_lib.register("adb_raster_project_fwd", [i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32,
+                                         vp, vp, vp, vp])
+_lib.register("adb_raster_scan_workspace_bytes", [i32, C.POINTER(C.c_size_t)])
+_lib.register("adb_raster_isect_scan", [i32, vp, vp, vp, C.c_size_t, vp])
+_lib.register("adb_raster_isect_emit", [i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp])
+_lib.register("adb_raster_sort_workspace_bytes", [i64, C.POINTER(C.c_size_t)])
+_lib.register("adb_raster_sort", [i64, i32, i32, i32, vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_int), vp])
+_lib.register("adb_raster_tile_offsets", [i64, vp, i32, i32, vp, vp])
+_lib.register("adb_raster_blend_fwd", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp])
+_lib.register("adb_raster_blend_bwd", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+_lib.register("adb_raster_project_bwd", [i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32,
+                                         vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+
+TILE = 16
+SPLAT_STRIDE = 12
+
+_ws_cache: dict = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    key = (dev.index, "ws")
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = t
+    return t
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H, eps2d, near, far, radius_clip):
+    """Projection + SH + tile counts for one camera.  Returns radii[N,2] i32, splats[N,12], tiles_per_gauss[N]."""
+    N = means.shape[0]
+    dev = means.device
+    radii = torch.empty(N, 2, dtype=torch.int32, device=dev)
+    splats = torch.empty(N, SPLAT_STRIDE, dtype=torch.float32, device=dev)
+    tpg = torch.empty(N, dtype=torch.int32, device=dev)
+    _lib.call("adb_raster_project_fwd", N, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
+              _lib.ptr(sh), int(sh_degree), _lib.ptr(viewmat), _lib.ptr(K), _lib.ptr(campos), W, H, eps2d, near, far,
+              radius_clip, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), _lib.stream())
+    return radii, splats, tpg
+
+
+def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True):
+    """Tile keys/values (sorted), tile offsets [T+1].  One host sync (reads the intersection count)."""
+    N = radii.shape[0]
+    dev = radii.device
+    T = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
+    offsets = torch.empty(T + 1, dtype=torch.int32, device=dev)
+    if N == 0:
+        offsets.zero_()
+        e64 = torch.empty(0, dtype=torch.int64, device=dev)
+        return e64, torch.empty(0, dtype=torch.int32, device=dev), offsets, 0
+    nb = C.c_size_t(0)
+    _lib.call("adb_raster_scan_workspace_bytes", N, C.byref(nb))
+    cum = torch.empty(N, dtype=torch.int64, device=dev)
+    ws = _workspace(dev, nb.value)
+    _lib.call("adb_raster_isect_scan", N, _lib.ptr(tpg), _lib.ptr(cum), _lib.ptr(ws), ws.numel(), _lib.stream())
+    n_isect = int(cum[-1].item())  # the pipeline's single host sync
+    keys_a = torch.empty(max(n_isect, 1), dtype=torch.int64, device=dev)
+    vals_a = torch.empty(max(n_isect, 1), dtype=torch.int32, device=dev)
+    if n_isect > 0:
+        _lib.call("adb_raster_isect_emit", N, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(cum), W, H, cam_id, n_cams,
+                  _lib.ptr(keys_a), _lib.ptr(vals_a), _lib.stream())
+    keys, vals = keys_a, vals_a
+    if sort and n_isect > 0:
+        keys_b, vals_b = torch.empty_like(keys_a), torch.empty_like(vals_a)
+        _lib.call("adb_raster_sort_workspace_bytes", n_isect, C.byref(nb))
+        ws = _workspace(dev, nb.value)
+        in_b = C.c_int(0)
+        _lib.call("adb_raster_sort", n_isect, W, H, n_cams, _lib.ptr(keys_a), _lib.ptr(vals_a), _lib.ptr(keys_b),
+                  _lib.ptr(vals_b), _lib.ptr(ws), ws.numel(), C.byref(in_b), _lib.stream())
+        if in_b.value:
+            keys, vals = keys_b, vals_b
+    _lib.call("adb_raster_tile_offsets", n_isect, _lib.ptr(keys), W, H, _lib.ptr(offsets), _lib.stream())
+    return keys[:n_isect], vals[:n_isect], offsets, n_isect
+
+
+def blend_forward(W, H, N, splats, vals, offsets):
+    dev = splats.device
+    colors = torch.empty(H, W, 4, dtype=torch.float32, device=dev)
+    alphas = torch.empty(H, W, dtype=torch.float32, device=dev)
+    last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
+    _lib.call("adb_raster_blend_fwd", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
+              _lib.ptr(offsets), _lib.ptr(colors), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.stream())
+    return colors, alphas, last_ids
+
+
+def blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas):
+    v_splats = torch.zeros(N, SPLAT_STRIDE, dtype=torch.float32, device=splats.device)
+    _lib.call("adb_raster_blend_bwd", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
+              _lib.ptr(offsets), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(v_colors), _lib.ptr(v_alphas),
+              _lib.ptr(v_splats), _lib.stream())
+    return v_splats
+
+
+class _RasterizeOneCamera(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, sh, colors_direct, viewmat, K, campos, W, H, sh_degree, eps2d,
+                near, far, radius_clip, cam_id, n_cams):
+        _lib.require_cuda(means)
+        N = means.shape[0]
+        with torch.cuda.device(means.device):
+            radii, splats, tpg = project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H,
+                                         eps2d, near, far, radius_clip)
+            if colors_direct is not None:
+                splats[:, 6:9] = colors_direct
+            keys, vals, offsets, n_isect = intersect(radii, splats, tpg, W, H, cam_id, n_cams)
+            colors, alphas, last_ids = blend_forward(W, H, N, splats, vals, offsets)
+        ctx.save_for_backward(means, quats, scales, opacities, sh, viewmat, K, campos, radii, splats, vals, offsets,
+                              alphas, last_ids)
+        ctx.cfg = (W, H, sh_degree, eps2d, near, far, radius_clip, colors_direct is not None)
+        ctx.mark_non_differentiable(radii, splats, tpg, keys, vals, offsets)
+        return colors, alphas, radii, splats, tpg, keys, vals, offsets
+
+    @staticmethod
+    def backward(ctx, v_colors, v_alphas, *_unused):
+        (means, quats, scales, opacities, sh, viewmat, K, campos, radii, splats, vals, offsets, alphas,
+         last_ids) = ctx.saved_tensors
+        W, H, sh_degree, eps2d, near, far, radius_clip, direct = ctx.cfg
+        N = means.shape[0]
+        dev = means.device
+        v_colors = torch.zeros(H, W, 4, device=dev) if v_colors is None else _f32c(v_colors)
+        v_alphas = torch.zeros(H, W, device=dev) if v_alphas is None else _f32c(v_alphas)
+        with torch.cuda.device(dev):
+            v_splats = blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas)
+            v_means = torch.empty_like(means)
+            v_quats = torch.empty_like(quats)
+            v_scales = torch.empty_like(scales)
+            v_opac = torch.empty_like(opacities)
+            v_sh = torch.empty_like(sh) if sh is not None else None
+            v_view = torch.zeros(4, 4, dtype=torch.float32, device=dev)
+            v_campos = torch.zeros(3, dtype=torch.float32, device=dev) if sh is not None else None
+            _lib.call("adb_raster_project_bwd", N, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(sh),
+                      int(sh_degree), _lib.ptr(viewmat), _lib.ptr(K), _lib.ptr(campos), W, H, eps2d, near, far,
+                      radius_clip, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(v_splats), _lib.ptr(v_means),
+                      _lib.ptr(v_quats), _lib.ptr(v_scales), _lib.ptr(v_opac), _lib.ptr(v_sh), _lib.ptr(v_view),
+                      _lib.ptr(v_campos), _lib.stream())
+        v_direct = None
+        if direct:
+            live = (radii > 0).any(-1, keepdim=True)
+            v_direct = v_splats[:, 6:9] * live
+        return (v_means, v_quats, v_scales, v_opac, v_sh, v_direct, v_view, None, v_campos,
+                None, None, None, None, None, None, None, None, None)
+
+
+def rasterization(means: torch.Tensor, quats: torch.Tensor, scales: torch.Tensor, opacities: torch.Tensor,
+                  colors: torch.Tensor, viewmats: torch.Tensor, Ks: torch.Tensor, width: int, height: int,
+                  near_plane: float = 0.01, far_plane: float = 1e10, radius_clip: float = 0.0, eps2d: float = 0.3,
+                  sh_degree: Optional[int] = None, packed: bool = False, tile_size: int = 16,
+                  backgrounds: Optional[torch.Tensor] = None, render_mode: str = "RGB",
+                  rasterize_mode: str = "classic", absgrad: bool = False, **unsupported):
+    """See module docstring.  ``colors`` is SH [N,K,3] when ``sh_degree`` is given, else RGB [N,3]."""
+    if unsupported:
+        raise NotImplementedError(f"rasterization(): unsupported arguments {sorted(unsupported)}")
+    if packed or absgrad or rasterize_mode != "classic" or tile_size != 16:
+        raise NotImplementedError("only packed=False, absgrad=False, rasterize_mode='classic', tile_size=16 "
+                                  "(the reference's configuration, h3dgsv3.py:664-680)")
+    if render_mode not in ("RGB", "RGB+D"):
+        raise NotImplementedError("render_mode must be 'RGB' or 'RGB+D'")
+    _lib.require_cuda(means)
+    N = means.shape[0]
+    C_ = viewmats.shape[0]
+    assert means.shape == (N, 3) and quats.shape == (N, 4) and scales.shape == (N, 3) and opacities.shape == (N,)
+    assert viewmats.shape == (C_, 4, 4) and Ks.shape == (C_, 3, 3)
+    means, quats, scales, opacities = _f32c(means), _f32c(quats), _f32c(scales), _f32c(opacities)
+    sh = direct = None
+    if sh_degree is not None:
+        assert colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3
+        if (sh_degree + 1) ** 2 > colors.shape[1]:
+            raise ValueError("sh_degree needs more SH coefficients than colors provides")
+        sh = _f32c(colors)
+        if sh.shape[1] != 16:  # kernel reads a fixed 16x3 block
+            sh = torch.cat([sh, sh.new_zeros(N, 16 - sh.shape[1], 3)], 1) if sh.shape[1] < 16 else sh[:, :16].contiguous()
+    else:
+        assert colors.shape == (N, 3)
+        direct = _f32c(colors)
+    out_c, out_a, radii_l, metas = [], [], [], []
+    base = 0
+    for c in range(C_):
+        V = _f32c(viewmats[c])
+        K = _f32c(Ks[c]).detach()
+        campos = torch.inverse(V)[:3, 3].contiguous() if sh is not None else None
+        col, alp, radii, splats, tpg, keys, vals, offs = _RasterizeOneCamera.apply(
+            means, quats, scales, opacities, sh, direct, V, K, campos, int(width), int(height),
+            int(sh_degree) if sh_degree is not None else 0, float(eps2d), float(near_plane), float(far_plane),
+            float(radius_clip), c, C_)
+        if backgrounds is not None:
+            col = torch.cat([col[..., :3] + (1.0 - alp[..., None]) * backgrounds[c].view(1, 1, 3), col[..., 3:]], -1)
+        out_c.append(col if render_mode == "RGB+D" else col[..., :3])
+        out_a.append(alp[..., None])
+        radii_l.append(radii)
+        metas.append((splats, tpg, keys, vals, offs + base))  # gsplat offsets index the concatenated list
+        base += int(vals.numel())
+    th, tw = (height + TILE - 1) // TILE, (width + TILE - 1) // TILE
+    meta = {
+        "radii": torch.stack(radii_l),
+        "means2d": torch.stack([m[0][:, 0:2] for m in metas]),
+        "depths": torch.stack([m[0][:, 9] for m in metas]),
+        "conics": torch.stack([m[0][:, 2:5] for m in metas]),
+        "opacities": opacities,
+        "tiles_per_gauss": torch.stack([m[1] for m in metas]),
+        "isect_ids": torch.cat([m[2] for m in metas]),
+        "flatten_ids": torch.cat([m[3] for m in metas]),
+        "isect_offsets": torch.stack([m[4][:-1].view(th, tw) for m in metas]),
+        "width": width, "height": height, "tile_size": TILE, "tile_width": tw, "tile_height": th, "n_cameras": C_,
+    }
+    return torch.stack(out_c), torch.stack(out_a), meta

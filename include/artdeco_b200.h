@@ -1,0 +1,77 @@
+/* artdeco_b200 — C ABI of the B200-native (sm_100a) kernels behind ARTDECO's hot-path operators.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says HOST; tensors are dense, row-major, fp32
+ *     unless typed otherwise; no allocation happens inside the library (the caller passes outputs and
+ *     workspaces); every entry point returns 0 on success, 1 = invalid argument, 2 = CUDA error,
+ *     3 = workspace too small, and adb_last_error() (HOST, thread-local) describes the failure;
+ *   - every launch goes to the `stream` argument (a cudaStream_t); nothing synchronises the device;
+ *   - each declaration cites the reference interface it replaces (paths relative to the ARTDECO tree).
+ *   INTEGRATION.md shows the ctypes / pybind binding a reference maintainer would add.
+ */
+#ifndef ARTDECO_B200_H
+#define ARTDECO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* adb_stream_t; /* == cudaStream_t */
+
+/* ---- library ---- */
+const char* adb_last_error(void);
+int adb_version(void);
+int adb_check_device(void); /* 0 iff the current device is compute capability 10.x */
+
+/* ---- fused SSIM ----
+ * replaces fused_ssim_cuda.fusedssim          Reconstruct/submodules/fused-ssim/ssim.cu:434-478 (ext.cpp:5)
+ *          fused_ssim_cuda.fusedssim_backward Reconstruct/submodules/fused-ssim/ssim.cu:480-517 (ext.cpp:6)
+ * img1,img2,[maps] are [B,CH,H,W].  ssim_map and ssim_sum may each be NULL (not both); ssim_sum (1 float,
+ * caller-zeroed) receives the sum of the map (the mean the Python wrapper returns, __init__.py:41-42).
+ * Backward: if dL_dmap is NULL every map element's upstream gradient is (dL_scalar ? *dL_scalar : 1)*dL_scale. */
+int adb_ssim_forward(int B, int CH, int H, int W, float C1, float C2, const float* img1, const float* img2,
+                     int train, float* ssim_map, float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12,
+                     float* ssim_sum, adb_stream_t stream);
+int adb_ssim_backward(int B, int CH, int H, int W, float C1, float C2, const float* img1, const float* img2,
+                      const float* dL_dmap, const float* dL_scalar, float dL_scale, const float* dm_dmu1,
+                      const float* dm_dsigma1_sq, const float* dm_dsigma12, float* dL_dimg1, adb_stream_t stream);
+
+/* ---- Gaussian-splat rasterizer (one camera per call) ----
+ * replaces the stages of gsplat.rendering.rasterization as called at
+ * Reconstruct/scene/scene_models/h3dgsv3.py:664-680 (gsplat itself is an un-vendored pip dependency).
+ * Layouts: see artdeco_b200/csrc/raster_common.cuh.  viewmat[16], K[9], campos[3] are DEVICE pointers. */
+int adb_raster_project_fwd(int N, const float* means, const float* quats, const float* scales,
+                           const float* opacities, const float* sh /*[N,16,3] or NULL*/, int sh_degree,
+                           const float* viewmat, const float* K, const float* campos, int W, int H, float eps2d,
+                           float near_plane, float far_plane, float radius_clip, int32_t* radii /*[N,2]*/,
+                           float* splats /*[N,12]*/, int32_t* tiles_per_gauss /*[N]*/, adb_stream_t stream);
+int adb_raster_scan_workspace_bytes(int N, size_t* bytes /*HOST*/);
+int adb_raster_isect_scan(int N, const int32_t* tiles_per_gauss, int64_t* cum_tiles /*[N] inclusive*/, void* ws,
+                          size_t ws_bytes, adb_stream_t stream);
+int adb_raster_isect_emit(int N, const int32_t* radii, const float* splats, const int64_t* cum_tiles, int W, int H,
+                          int cam_id, int n_cams, int64_t* keys, int32_t* vals, adb_stream_t stream);
+int adb_raster_sort_workspace_bytes(long long n_isect, size_t* bytes /*HOST*/);
+int adb_raster_sort(long long n_isect, int W, int H, int n_cams, int64_t* keys_a, int32_t* vals_a, int64_t* keys_b,
+                    int32_t* vals_b, void* ws, size_t ws_bytes, int* sorted_in_b /*HOST*/, adb_stream_t stream);
+int adb_raster_tile_offsets(long long n_isect, const int64_t* keys_sorted, int W, int H,
+                            int32_t* tile_offsets /*[T+1]*/, adb_stream_t stream);
+int adb_raster_blend_fwd(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                         const int32_t* tile_offsets, float* colors /*[H,W,4]*/, float* alphas /*[H,W]*/,
+                         int32_t* last_ids /*[H,W]*/, adb_stream_t stream);
+int adb_raster_blend_bwd(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                         const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
+                         const float* v_colors, const float* v_alphas, float* v_splats /*[N,12] zeroed, +=*/,
+                         adb_stream_t stream);
+int adb_raster_project_bwd(int N, const float* means, const float* quats, const float* scales, const float* sh,
+                           int sh_degree, const float* viewmat, const float* K, const float* campos, int W, int H,
+                           float eps2d, float near_plane, float far_plane, float radius_clip, const int32_t* radii,
+                           const float* splats, const float* v_splats, float* v_means, float* v_quats,
+                           float* v_scales, float* v_opac, float* v_sh, float* v_viewmat /*[16] +=*/,
+                           float* v_campos /*[3] +=*/, adb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -140,7 +140,7 @@ static int project_one(const float* mean, const float* quat, const float* scale,
     c = c + cam->eps2d;
     float det = a * c - b * b;
     st->a = a; st->b = b; st->c = c; st->det = det;
-    if (det <= 0.f) return 0;
+    if (!(det > 0.f)) return 0;
     float u = fx * x * rz + cx, v = fy * y * rz + cy;
 
     if (opacity < ALPHA_THRESHOLD) return 0;

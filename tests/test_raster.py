@@ -1,0 +1,152 @@
+"""Rasterizer parity (GPU, through the C ABI) against the C oracle, stage by stage and end to end.
+
+Contracts (BASELINE.json north_star):
+  * integer work — radii, tile counts, tile keys, sort order (values), tile offsets, last_ids — BIT-EXACT;
+  * float work — splat records, colours/depth/alpha, every gradient — within 1e-4 of the tensor's scale.
+The blend's discrete decisions (alpha < 1/255 skip, T <= 1e-4 stop) are evaluated with ex2.approx on the GPU and
+expf on the CPU, so a handful of pixels may legitimately take the other branch: the image/gradient checks admit
+an outlier fraction of 1e-4 and report the count."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from artdeco_b200 import synthetic
+from helpers import assert_close, rel_err
+
+KEYS = ("means", "quats", "scales", "opacities", "sh")
+
+
+def _scene(N, W, H, seed=0, view=2.0, **kw):
+    sc = synthetic.raster_scene(N, seed=seed, **kw)
+    V, K = synthetic.camera(W, H, view=view)
+    return sc, V, K
+
+
+def _gpu_stages(sc, V, K, W, H, dev):
+    from artdeco_b200 import rasterization as R
+    t = {k: sc[k].to(dev) for k in KEYS}
+    Vd, Kd = V.to(dev), K.to(dev)
+    campos = torch.inverse(Vd)[:3, 3].contiguous()
+    radii, splats, tpg = R.project(t["means"], t["quats"], t["scales"], t["opacities"], t["sh"], 3, Vd, Kd, campos, W,
+                                   H, 0.01, 0.01, 1e10, 0.0)
+    keys, vals, offs, n = R.intersect(radii, splats, tpg, W, H)
+    colors, alphas, last = R.blend_forward(W, H, radii.shape[0], splats, vals, offs)
+    return dict(radii=radii, splats=splats, tpg=tpg, keys=keys, vals=vals, offs=offs, colors=colors, alphas=alphas,
+                last=last, n=n, t=t, V=Vd, K=Kd, campos=campos)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,W,H,view", [(3000, 320, 192, 1.0), (20000, 640, 360, 5.0), (100000, 1920, 1080, 3.5)])
+def test_forward_stages_match_oracle(cuda, N, W, H, view):
+    sc, V, K = _scene(N, W, H, seed=7 if N == 3000 else 0, view=view)
+    f = oracle.rasterize_fwd(*[sc[k].numpy() for k in KEYS], V.numpy(), K.numpy(), W, H)
+    g = _gpu_stages(sc, V, K, W, H, cuda)
+    # --- bit-exact integer contract ---
+    assert np.array_equal(g["radii"].cpu().numpy(), f["radii"]), "radii"
+    assert np.array_equal(g["tpg"].cpu().numpy(), f["tiles_per_gauss"]), "tiles_per_gauss"
+    assert g["n"] == len(f["keys"])
+    assert np.array_equal(g["keys"].cpu().numpy(), f["keys"]), "sorted tile keys"
+    assert np.array_equal(g["vals"].cpu().numpy(), f["vals"]), "sort indices"
+    assert np.array_equal(g["offs"].cpu().numpy()[:-1], f["tile_offsets"]), "tile offsets"
+    assert int(g["offs"][-1]) == g["n"]
+    # --- float contract on the splat record (visible Gaussians only) ---
+    vis = (f["radii"] > 0).any(1)
+    sp = g["splats"].cpu().numpy()[vis]
+    assert np.array_equal(sp[:, 0:2], f["means2d"][vis]) and np.array_equal(sp[:, 9], f["depths"][vis]), \
+        "projection is compiled without FMA contraction and must be bit-identical to the oracle"
+    assert np.array_equal(sp[:, 2:5], f["conics"][vis])
+    assert_close(sp[:, 6:9], f["rgb"][vis], what="sh colours")
+    # --- image ---
+    assert_close(g["colors"], f["colors"], what="colors", max_outlier_frac=1e-4)
+    assert_close(g["alphas"], f["alphas"], what="alphas", max_outlier_frac=1e-4)
+    mism = (g["last"].cpu().numpy() != f["last_ids"]).mean()
+    assert mism <= 1e-4, f"last_ids differ on {mism:.2e} of pixels"
+
+
+@pytest.mark.gpu
+def test_golden_fixture_bit_exact(cuda):
+    import pathlib
+    gf = np.load(pathlib.Path(__file__).parent / "golden" / "raster_small.npz")
+    sc, V, K = _scene(int(gf["N"]), int(gf["W"]), int(gf["H"]), seed=int(gf["seed"]), view=float(gf["view"]))
+    g = _gpu_stages(sc, V, K, int(gf["W"]), int(gf["H"]), cuda)
+    assert np.array_equal(g["radii"].cpu().numpy(), gf["radii"])
+    assert np.array_equal(g["keys"].cpu().numpy(), gf["keys"])
+    assert np.array_equal(g["vals"].cpu().numpy(), gf["vals"])
+    assert np.array_equal(g["offs"].cpu().numpy()[:-1], gf["tile_offsets"])
+    assert_close(g["colors"], gf["colors"], what="colors", max_outlier_frac=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,W,H", [(4000, 320, 192), (50000, 960, 540)])
+def test_backward_matches_oracle(cuda, N, W, H):
+    from artdeco_b200 import rasterization as R
+    sc, V, K = _scene(N, W, H, seed=11, view=5.0, scale_range=(0.01, 0.15))
+    args = [sc[k].numpy() for k in KEYS]
+    f = oracle.rasterize_fwd(*args, V.numpy(), K.numpy(), W, H)
+    vc, va = synthetic.upstream_grads(W, H, seed=1)
+    b = oracle.rasterize_bwd(*args, V.numpy(), f, vc[0].numpy(), va[0, ..., 0].numpy())
+
+    t = {k: sc[k].to(cuda).requires_grad_(True) for k in KEYS}
+    Vd = V.to(cuda).requires_grad_(True)
+    colors, alphas, meta = R.rasterization(t["means"], t["quats"], t["scales"], t["opacities"], t["sh"], Vd[None],
+                                           K.to(cuda)[None], W, H, render_mode="RGB+D", sh_degree=3, eps2d=0.01)
+    ((colors * vc.to(cuda)).sum() + (alphas * va.to(cuda)).sum()).backward()
+    fr = 2e-4  # gradient tensors: a flipped blend decision moves a few Gaussians' gradients
+    assert_close(t["means"].grad, b["v_means"], what="v_means", max_outlier_frac=fr)
+    assert_close(t["quats"].grad, b["v_quats"], what="v_quats", max_outlier_frac=fr)
+    assert_close(t["scales"].grad, b["v_scales"], what="v_scales", max_outlier_frac=fr)
+    assert_close(t["opacities"].grad, b["v_opac"], what="v_opac", max_outlier_frac=fr)
+    assert_close(t["sh"].grad, b["v_sh"], what="v_sh", max_outlier_frac=fr)
+    Vt = V.double().requires_grad_(True)
+    (torch.inverse(Vt)[:3, 3] * torch.tensor(b["v_campos"], dtype=torch.float64)).sum().backward()
+    vV = b["v_viewmat"].astype(np.float64) + Vt.grad.numpy()
+    assert rel_err(Vd.grad.cpu().numpy()[:3], vV[:3]) < 1e-3, "viewmat gradient (sum over all Gaussians)"
+
+
+@pytest.mark.gpu
+def test_edge_cases(cuda):
+    from artdeco_b200 import rasterization as R
+    V, K = synthetic.camera(70, 50, focal=50.0)  # ragged: not a multiple of 16
+    z = lambda *s: torch.zeros(*s, device=cuda)
+    c, a, meta = R.rasterization(z(0, 3), z(0, 4), z(0, 3), z(0), z(0, 16, 3), V.to(cuda)[None], K.to(cuda)[None], 70, 50,
+                                 render_mode="RGB+D", sh_degree=3, eps2d=0.01)
+    assert c.shape == (1, 50, 70, 4) and not c.any() and not a.any() and meta["radii"].shape == (1, 0, 2)
+    means = torch.tensor([[0, 0, -1.0], [0, 0, 5.0], [500.0, 0, 5.0], [0, 0, 5.0]], device=cuda)
+    quats = torch.tensor([[1.0, 0, 0, 0]], device=cuda).repeat(4, 1)
+    scales = torch.full((4, 3), 0.1, device=cuda)
+    opac = torch.tensor([0.9, 0.001, 0.9, 0.9], device=cuda)
+    c, a, meta = R.rasterization(means, quats, scales, opac, z(4, 16, 3), V.to(cuda)[None], K.to(cuda)[None], 70, 50,
+                                 render_mode="RGB+D", sh_degree=3, eps2d=0.01)
+    assert (meta["radii"][0, :3] == 0).all() and (meta["radii"][0, 3] > 0).all()
+    f = oracle.rasterize_fwd(means.cpu().numpy(), quats.cpu().numpy(), scales.cpu().numpy(), opac.cpu().numpy(),
+                             np.zeros((4, 16, 3), np.float32), V.numpy(), K.numpy(), 70, 50)
+    assert_close(c[0], f["colors"], what="ragged colors")
+    assert_close(a[0, ..., 0], f["alphas"], what="ragged alphas")
+
+
+@pytest.mark.gpu
+def test_full_size_properties_1m_1080p(cuda):
+    """BASELINE size (1M Gaussians, 1080p): size-independent properties instead of the (slow) oracle."""
+    from artdeco_b200 import rasterization as R
+    sc, V, K = _scene(1_000_000, 1920, 1080, seed=0, view=3.5)
+    g = _gpu_stages(sc, V, K, 1920, 1080, cuda)
+    keys, vals, offs = g["keys"], g["vals"], g["offs"]
+    assert g["n"] == int(g["tpg"].sum()) > 1_000_000
+    assert bool((keys[1:] >= keys[:-1]).all()), "sortedness"
+    same = keys[1:] == keys[:-1]
+    assert bool((vals[1:][same] > vals[:-1][same]).all()), "stability"
+    tiles = keys >> 32
+    T = 120 * 68
+    assert bool((offs.long()[:-1] == torch.searchsorted(tiles, torch.arange(T, device=cuda))).all())
+    # multiset of values is a permutation of the emission (every Gaussian appears tiles_per_gauss times)
+    counts = torch.bincount(vals.long(), minlength=1_000_000)
+    assert torch.equal(counts, g["tpg"].long())
+    a = g["alphas"]
+    assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0 - 1e-4 + 1e-6
+    assert torch.isfinite(g["colors"]).all()
+    # linearity of the blend in the feature channels: doubling rgb/depth doubles the image
+    sp2 = g["splats"].clone()
+    sp2[:, 6:10] *= 2
+    c2, a2, _ = R.blend_forward(1920, 1080, 1_000_000, sp2, vals, offs)
+    assert torch.equal(a2, a) and torch.allclose(c2, 2 * g["colors"], rtol=1e-6, atol=0)
