@@ -7,8 +7,8 @@ There is no CPU implementation: every operator raises unless a CUDA sm_100 devic
 ``libartdeco_b200.so`` are available.
 """
 from . import _lib  # noqa: F401
-from . import rasterization as _rasterization_mod  # noqa: F401  (registers C signatures)
-from .rasterization import rasterization  # noqa: F401
+from . import raster  # noqa: F401  (registers C signatures)
+from .raster import rasterization  # noqa: F401
 from .ssim import FusedSSIMMap, fused_ssim, fusedssim, fusedssim_backward  # noqa: F401
 
 __version__ = "0.1.0"

@@ -72,8 +72,46 @@ def lib() -> C.CDLL:
     return _lib
 
 
+# Kernel launches issued by one call of each entry point (CUB launches counted for scan/sort).
+LAUNCHES = {
+    "adb_ssim_forward": 1, "adb_ssim_backward": 1, "adb_raster_project_fwd": 1, "adb_raster_isect_scan": 2,
+    "adb_raster_isect_emit": 1, "adb_raster_sort": 8, "adb_raster_tile_offsets": 1, "adb_raster_blend_fwd": 1,
+    "adb_raster_blend_bwd": 1, "adb_raster_project_bwd": 1,
+}
+
+
+class StageTimer:
+    """Optional per-entry-point device timing (CUDA events on the launching stream) and launch counting, used by
+    bench.py to report the dominant kernel's live duration.  Off by default: zero overhead on the product path."""
+
+    def __init__(self):
+        self.events: dict[str, list] = {}
+        self.launches = 0
+
+    def reset(self):
+        self.events.clear()
+        self.launches = 0
+
+    def totals_ms(self) -> dict[str, tuple[float, int]]:
+        out = {}
+        for k, evs in self.events.items():
+            out[k] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+        return out
+
+
+TIMER: StageTimer | None = None
+
+
 def call(name: str, *args) -> None:
-    rc = getattr(lib(), name)(*args)
+    if TIMER is not None and name in LAUNCHES:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib(), name)(*args)
+        b.record()
+        TIMER.events.setdefault(name, []).append((a, b))
+        TIMER.launches += LAUNCHES[name]
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         msg = lib().adb_last_error()
         raise ArtdecoB200Error(f"{name} failed (status {rc}): {msg.decode() if msg else '?'}")
@@ -86,7 +124,9 @@ def require_cuda(t: torch.Tensor | None = None) -> None:
     """Fail loudly when there is no sm_100 device: the product path has no CPU implementation."""
     if not torch.cuda.is_available():
         raise ArtdecoB200Error("artdeco_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    dev = t.device.index if (t is not None and t.is_cuda) else torch.cuda.current_device()
+    if t is not None and not t.is_cuda:
+        raise ArtdecoB200Error("expected a CUDA tensor: artdeco_b200 has no CPU implementation")
+    dev =t.device.index if (t is not None and t.is_cuda) else torch.cuda.current_device()
     if dev not in _checked_devices:
         with torch.cuda.device(dev):
             call("adb_check_device")

@@ -24,7 +24,7 @@ def _scene(N, W, H, seed=0, view=2.0, **kw):
 
 
 def _gpu_stages(sc, V, K, W, H, dev):
-    from artdeco_b200 import rasterization as R
+    from artdeco_b200 import raster as R
     t = {k: sc[k].to(dev) for k in KEYS}
     Vd, Kd = V.to(dev), K.to(dev)
     campos = torch.inverse(Vd)[:3, 3].contiguous()
@@ -80,7 +80,7 @@ def test_golden_fixture_bit_exact(cuda):
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,W,H", [(4000, 320, 192), (50000, 960, 540)])
 def test_backward_matches_oracle(cuda, N, W, H):
-    from artdeco_b200 import rasterization as R
+    from artdeco_b200 import raster as R
     sc, V, K = _scene(N, W, H, seed=11, view=5.0, scale_range=(0.01, 0.15))
     args = [sc[k].numpy() for k in KEYS]
     f = oracle.rasterize_fwd(*args, V.numpy(), K.numpy(), W, H)
@@ -106,7 +106,7 @@ def test_backward_matches_oracle(cuda, N, W, H):
 
 @pytest.mark.gpu
 def test_edge_cases(cuda):
-    from artdeco_b200 import rasterization as R
+    from artdeco_b200 import raster as R
     V, K = synthetic.camera(70, 50, focal=50.0)  # ragged: not a multiple of 16
     z = lambda *s: torch.zeros(*s, device=cuda)
     c, a, meta = R.rasterization(z(0, 3), z(0, 4), z(0, 3), z(0), z(0, 16, 3), V.to(cuda)[None], K.to(cuda)[None], 70, 50,
@@ -128,7 +128,7 @@ def test_edge_cases(cuda):
 @pytest.mark.gpu
 def test_full_size_properties_1m_1080p(cuda):
     """BASELINE size (1M Gaussians, 1080p): size-independent properties instead of the (slow) oracle."""
-    from artdeco_b200 import rasterization as R
+    from artdeco_b200 import raster as R
     sc, V, K = _scene(1_000_000, 1920, 1080, seed=0, view=3.5)
     g = _gpu_stages(sc, V, K, 1920, 1080, cuda)
     keys, vals, offs = g["keys"], g["vals"], g["offs"]

@@ -38,7 +38,9 @@ def test_fused_ssim_matches_oracle(cuda, shape, padding):
     a_gpu = a.to(cuda).requires_grad_(True)
     out = fused_ssim(a_gpu, b.to(cuda), padding=padding)
     out.backward()
-    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
+    # rtol 1e-5 as in the reference test, plus an fp32 floor: the map has O(1) entries of both signs, so for random
+    # images the mean is ~1e-4 and an fp32 sum cannot resolve it to 1e-5 relative (observed |err| ~2e-8).
+    assert abs(float(out.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach())) + 2e-7
     assert_close(a_gpu.grad, a_ref.grad, what="dL/dimg1")
 
 
