@@ -1,13 +1,19 @@
 """artdeco_b200 — B200-native (sm_100a) kernels behind ARTDECO's hot-path operator surface.
 
 Public operators (same names / argument meaning as the reference's, see each module's docstring):
-  ssim.fused_ssim, ssim.FusedSSIMMap, ssim.fusedssim, ssim.fusedssim_backward
-  rasterization.rasterization                      (gsplat.rendering.rasterization as ARTDECO calls it)
+  ssim.fused_ssim, ssim.FusedSSIMMap, ssim.fusedssim, ssim.fusedssim_backward      (fused_ssim)
+  raster.rasterization                                 (gsplat.rendering.rasterization as ARTDECO calls it)
+  adam.adamUpdate, adam.adamUpdateBasic                (diff_gaussian_rasterization, on-the-fly-nvs fork)
+  knn.distCUDA2, knn.distIndex2, knn.distIndexQ        (simple_knn._C)
+  cull.lod_select, cull.lod_cull                       (SceneModel.render's d_max cull)
 There is no CPU implementation: every operator raises unless a CUDA sm_100 device and the C-ABI library
 ``libartdeco_b200.so`` are available.
 """
 from . import _lib  # noqa: F401
-from . import raster  # noqa: F401  (registers C signatures)
+from . import adam, cull, knn, raster  # noqa: F401  (each registers its C signatures)
+from .adam import adamUpdate, adamUpdateBasic  # noqa: F401
+from .cull import lod_cull, lod_select  # noqa: F401
+from .knn import distCUDA2, distIndex2, distIndexQ  # noqa: F401
 from .raster import rasterization  # noqa: F401
 from .ssim import FusedSSIMMap, fused_ssim, fusedssim, fusedssim_backward  # noqa: F401
 

@@ -4,14 +4,16 @@
 //   inputs   means[N,3] quats[N,4] (wxyz) scales[N,3] opacities[N] sh[N,16,3]
 //            viewmat[16] (row-major world->camera), K[9], campos[3]   -- DEVICE pointers (no host sync)
 //   splats   [N,12] packed per-Gaussian record written by the projection and gathered (3x LDG.128) by the
-//            blend kernels:  0 mx | 1 my | 2 conic_a | 3 conic_b | 4 conic_c | 5 opacity |
-//                            6 r  | 7 g  | 8 b       | 9 depth   | 10,11 unused
+//            blend kernels:  0 mx | 1 my | 2 conic_a | 3 conic_b |
+//                            4 conic_c | 5 opacity | 6 sigma_max = ln(255*opacity)+0.02 | 7 bits: rx | ry<<16 |
+//                            8 r  | 9 g  | 10 b | 11 depth
 //   radii    int32[N,2]   (0,0) == culled; culled Gaussians have no splat record and emit no keys
 //   keys     int64[I]  (cam << (32+tile_bits)) | (tile << 32) | float_bits(depth);   vals int32[I] = cam*N + gaussian
 //   tile_offsets int32[T+1]  first sorted index of each tile, [T] = I
 //   colors   [H,W,4] = (r,g,b, sum z*alpha*T);  alphas [H,W];  last_ids int32[H,W]
-//   v_splats [N,12] gradient accumulators in the same slot order as `splats` (0,1 v_mean2d | 2..4 v_conic |
-//            5 v_opacity | 6..8 v_rgb | 9 v_depth), zeroed by the caller before blend_bwd.
+//   v_splats [N,12] per-Gaussian accumulators written by blend_bwd (zeroed by the caller first):
+//            0 M1x | 1 M1y | 2 M2xx | 3 M2xy | 4 M2yy | 5 M0   raw moments sum_p v_sigma * {dx,dy,dx^2,dxdy,dy^2,1}
+//            (project_bwd converts them to v_mean2d / v_conic / v_opacity) | 6..8 v_rgb | 9 v_depth | 10,11 unused.
 #pragma once
 #include "common.cuh"
 

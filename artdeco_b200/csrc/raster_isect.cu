@@ -27,7 +27,7 @@ isect_emit_kernel(int N, const int32_t* __restrict__ radii, const float* __restr
     const int2 r = reinterpret_cast<const int2*>(radii)[i];
     if (r.x <= 0 && r.y <= 0) return;
     const float4 rec0 = reinterpret_cast<const float4*>(splats + (size_t)i * ADB_SPLAT_STRIDE)[0];
-    const float depth = splats[(size_t)i * ADB_SPLAT_STRIDE + 9];
+    const float depth = splats[(size_t)i * ADB_SPLAT_STRIDE + 11];
     const int tw = (W + ADB_TILE - 1) / ADB_TILE, th = (H + ADB_TILE - 1) / ADB_TILE;
     float mx = rec0.x / (float)ADB_TILE, my = rec0.y / (float)ADB_TILE;
     float trx = (float)r.x / (float)ADB_TILE, try_ = (float)r.y / (float)ADB_TILE;

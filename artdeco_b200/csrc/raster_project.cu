@@ -58,7 +58,7 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
     const float m0 = means[3 * i], m1 = means[3 * i + 1], m2 = means[3 * i + 2];
 
     int rx_i = 0, ry_i = 0, count = 0;
-    float u = 0.f, v = 0.f, ca = 0.f, cb = 0.f, cc = 0.f;
+    float u = 0.f, v = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, lg = 0.f;
     const float x = R[0] * m0 + R[1] * m1 + R[2] * m2 + t[0];
     const float y = R[3] * m0 + R[4] * m1 + R[5] * m2 + t[1];
     const float z = R[6] * m0 + R[7] * m1 + R[8] * m2 + t[2];
@@ -110,7 +110,8 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
         if (ok) {
             u = fx * x * rz + cx;
             v = fy * y * rz + cy;
-            float ext = sqrtf(2.0f * adb_det_logf(opacity / ADB_ALPHA_THRESHOLD));
+            lg = adb_det_logf(opacity / ADB_ALPHA_THRESHOLD);
+            float ext = sqrtf(2.0f * lg);
             ext = fminf(3.33f, ext);
             float bb = 0.5f * (a + c);
             float lam = bb + sqrtf(fmaxf(0.01f, bb * bb - det));
@@ -158,9 +159,12 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
         r = fmaxf(r + 0.5f, 0.f); g = fmaxf(g + 0.5f, 0.f); bl = fmaxf(bl + 0.5f, 0.f);
     }
     float4* out = reinterpret_cast<float4*>(splats + (size_t)i * ADB_SPLAT_STRIDE);
+    // sigma <= ln(255*opacity) <=> alpha >= 1/255; the margin keeps the pre-test a strict superset of the exact test
+    const float sigma_max = lg + 0.02f;
+    const unsigned packed_radii = (unsigned)min(rx_i, 65535) | ((unsigned)min(ry_i, 65535) << 16);
     out[0] = make_float4(u, v, ca, cb);
-    out[1] = make_float4(cc, opacity, r, g);
-    out[2] = make_float4(bl, z, 0.f, 0.f);
+    out[1] = make_float4(cc, opacity, sigma_max, __uint_as_float(packed_radii));
+    out[2] = make_float4(r, g, bl, z);
 }
 
 }  // namespace

@@ -137,8 +137,11 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
         const float4 g1 = reinterpret_cast<const float4*>(v_splats + (size_t)i * ADB_SPLAT_STRIDE)[1];
         const float4 g2 = reinterpret_cast<const float4*>(v_splats + (size_t)i * ADB_SPLAT_STRIDE)[2];
         const float A = rec0.z, B = rec0.w, C = rec1.x;
-        const float vu = g0.x, vv = g0.y, gA = g0.z, gB = 0.5f * g0.w, gC = g1.x;
-        vo = g1.y;
+        // blend_bwd accumulates raw moments of v_sigma about the splat centre (slots 0..5 = M1x M1y M2xx M2xy M2yy M0):
+        //   v_mean2d = conic * (M1x, M1y);  v_conic = (M2xx/2, M2xy, M2yy/2);  v_opacity = -M0 / opacity
+        const float vu = A * g0.x + B * g0.y, vv = B * g0.x + C * g0.y;
+        const float gA = 0.5f * g0.z, gB = 0.5f * g0.w, gC = 0.5f * g1.x;
+        vo = -g1.y / rec1.y;
         const float v_rgb[3] = {g1.z, g1.w, g2.x};
         const float v_depth = g2.y;
 
@@ -212,7 +215,7 @@ project_bwd_kernel(int N, const float* __restrict__ means, const float* __restri
             const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
             float Bs[16], Bx[16], By[16], Bz[16];
             sh_basis_and_grad(sh_degree, nx, ny, nz, Bs, Bx, By, Bz);
-            const float rgb[3] = {rec1.z, rec1.w, rec2.x};
+            const float rgb[3] = {rec2.x, rec2.y, rec2.z};
             float gch[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) gch[c] = rgb[c] > 0.f ? v_rgb[c] : 0.f;

@@ -127,7 +127,7 @@ class _RasterizeOneCamera(torch.autograd.Function):
             radii, splats, tpg = project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H,
                                          eps2d, near, far, radius_clip)
             if colors_direct is not None:
-                splats[:, 6:9] = colors_direct
+                splats[:, 8:11] = colors_direct
             keys, vals, offsets, n_isect = intersect(radii, splats, tpg, W, H, cam_id, n_cams)
             colors, alphas, last_ids = blend_forward(W, H, N, splats, vals, offsets)
         ctx.save_for_backward(means, quats, scales, opacities, sh, viewmat, K, campos, radii, splats, vals, offsets,
@@ -219,7 +219,7 @@ def rasterization(means: torch.Tensor, quats: torch.Tensor, scales: torch.Tensor
     meta = {
         "radii": torch.stack(radii_l),
         "means2d": torch.stack([m[0][:, 0:2] for m in metas]),
-        "depths": torch.stack([m[0][:, 9] for m in metas]),
+        "depths": torch.stack([m[0][:, 11] for m in metas]),
         "conics": torch.stack([m[0][:, 2:5] for m in metas]),
         "opacities": opacities,
         "tiles_per_gauss": torch.stack([m[1] for m in metas]),

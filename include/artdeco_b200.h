@@ -71,6 +71,33 @@ int adb_raster_project_bwd(int N, const float* means, const float* quats, const 
                            float* v_scales, float* v_opac, float* v_sh, float* v_viewmat /*[16] +=*/,
                            float* v_campos /*[3] +=*/, adb_stream_t stream);
 
+/* ---- sparse Adam (in place, no bias correction) ----
+ * replaces diff_gaussian_rasterization.adamUpdate / adamUpdateBasic (on-the-fly-nvs fork, un-vendored); call sites
+ * Reconstruct/scene/optimizers.py:48-57 (Basic), 90-99, 116-128, 144-156.  visible: uint8/bool [N] or NULL;
+ * lr_dev: NULL (use lr_scalar) or a device tensor of numel 1, N or N*M. */
+int adb_adam_update(long long N, long long M, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                    const unsigned char* visible, const float* lr_dev, long long lr_numel, float lr_scalar, float b1,
+                    float b2, float eps, adb_stream_t stream);
+
+/* ---- LoD d_max cull: mask + fade ratio + compacted ascending ids ----
+ * replaces the torch block at Reconstruct/scene/scene_models/h3dgsv3.py:626-645 (and the scan at :942-953).
+ * count is a DEVICE int32; ids has capacity N; ratio may be NULL. */
+int adb_lod_select_workspace_bytes(long long N, size_t* bytes /*HOST*/);
+int adb_lod_select(long long N, const float* xyz, const float* d_max, const float* cam /*[3]*/, unsigned char* mask,
+                   float* ratio, int32_t* ids, int32_t* count, void* ws, size_t ws_bytes, adb_stream_t stream);
+
+/* ---- exact KNN on a grid hash ----
+ * replaces SimpleKNN::knn (distCUDA2)        Reconstruct/submodules/simple-knn/simple_knn.cu:188-224, spatial.cu:16-26
+ *          SimpleKNN::knn_index2 (distIndex2) simple_knn.cu:468-522, spatial.cu:29-41
+ *          SimpleKNN::knn_indexQ (distIndexQ) simple_knn.cu:592-651, spatial.cu:44-58
+ * points [P,3]; squared distances; rows sorted ascending; unfilled slots FLT_MAX / -1; K <= 32. */
+int adb_knn_workspace_bytes(long long P, size_t* bytes /*HOST*/);
+int adb_knn_mean3(long long P, const float* points, float* mean_dists /*[P]*/, void* ws, size_t ws_bytes,
+                  adb_stream_t stream);
+int adb_knn_index(long long P, const float* points, int K, long long Q, const int32_t* query_idx /*[Q] or NULL*/,
+                  const unsigned char* candidate /*[P] or NULL*/, float* dists /*[Q*K]*/, int32_t* ids /*[Q*K]*/,
+                  void* ws, size_t ws_bytes, adb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

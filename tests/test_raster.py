@@ -53,10 +53,10 @@ def test_forward_stages_match_oracle(cuda, N, W, H, view):
     # --- float contract on the splat record (visible Gaussians only) ---
     vis = (f["radii"] > 0).any(1)
     sp = g["splats"].cpu().numpy()[vis]
-    assert np.array_equal(sp[:, 0:2], f["means2d"][vis]) and np.array_equal(sp[:, 9], f["depths"][vis]), \
+    assert np.array_equal(sp[:, 0:2], f["means2d"][vis]) and np.array_equal(sp[:, 11], f["depths"][vis]), \
         "projection is compiled without FMA contraction and must be bit-identical to the oracle"
     assert np.array_equal(sp[:, 2:5], f["conics"][vis])
-    assert_close(sp[:, 6:9], f["rgb"][vis], what="sh colours")
+    assert_close(sp[:, 8:11], f["rgb"][vis], what="sh colours")
     # --- image ---
     assert_close(g["colors"], f["colors"], what="colors", max_outlier_frac=1e-4)
     assert_close(g["alphas"], f["alphas"], what="alphas", max_outlier_frac=1e-4)
@@ -147,6 +147,6 @@ def test_full_size_properties_1m_1080p(cuda):
     assert torch.isfinite(g["colors"]).all()
     # linearity of the blend in the feature channels: doubling rgb/depth doubles the image
     sp2 = g["splats"].clone()
-    sp2[:, 6:10] *= 2
+    sp2[:, 8:12] *= 2
     c2, a2, _ = R.blend_forward(1920, 1080, 1_000_000, sp2, vals, offs)
     assert torch.equal(a2, a) and torch.allclose(c2, 2 * g["colors"], rtol=1e-6, atol=0)

@@ -1,0 +1,34 @@
+"""Minimal driver for ncu: runs a few device-resident fwd+bwd steps of the bench workload (no e2e, no CPU leg)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from artdeco_b200 import _lib, synthetic  # noqa: E402
+from artdeco_b200 import raster as R  # noqa: E402
+
+N = int(os.environ.get("ADB_N", "1000000"))
+steps = int(os.environ.get("ADB_STEPS", "3"))
+W, H = 1920, 1080
+dev = torch.device("cuda:0")
+sc = synthetic.raster_scene(N, seed=0)
+V, K = synthetic.camera(W, H, view=3.5)
+vc, va = synthetic.upstream_grads(W, H, seed=1)
+t = {k: sc[k].to(dev) for k in ("means", "quats", "scales", "opacities", "sh")}
+Vd, Kd, vcd, vad = V.to(dev), K.to(dev), vc[0].contiguous().to(dev), va[0, ..., 0].contiguous().to(dev)
+campos = torch.inverse(Vd)[:3, 3].contiguous()
+gm, gq, gs, go, gsh = (torch.empty_like(t[k]) for k in ("means", "quats", "scales", "opacities", "sh"))
+vv, vcp = torch.zeros(4, 4, device=dev), torch.zeros(3, device=dev)
+for _ in range(steps):
+    radii, splats, tpg = R.project(t["means"], t["quats"], t["scales"], t["opacities"], t["sh"], 3, Vd, Kd, campos, W, H,
+                                   0.01, 0.01, 1e10, 0.0)
+    keys, vals, offs, n = R.intersect(radii, splats, tpg, W, H)
+    colors, alphas, last = R.blend_forward(W, H, N, splats, vals, offs)
+    v_splats = R.blend_backward(W, H, N, splats, vals, offs, alphas, last, vcd, vad)
+    _lib.call("adb_raster_project_bwd", N, _lib.ptr(t["means"]), _lib.ptr(t["quats"]), _lib.ptr(t["scales"]),
+              _lib.ptr(t["sh"]), 3, _lib.ptr(Vd), _lib.ptr(Kd), _lib.ptr(campos), W, H, 0.01, 0.01, 1e10, 0.0,
+              _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(v_splats), _lib.ptr(gm), _lib.ptr(gq), _lib.ptr(gs),
+              _lib.ptr(go), _lib.ptr(gsh), _lib.ptr(vv), _lib.ptr(vcp), _lib.stream())
+torch.cuda.synchronize()
+print("n_isect", n)
