@@ -10,7 +10,7 @@ There is no CPU implementation: every operator raises unless a CUDA sm_100 devic
 ``libartdeco_b200.so`` are available.
 """
 from . import _lib  # noqa: F401
-from . import adam, cull, knn, raster  # noqa: F401  (each registers its C signatures)
+from . import adam, cull, knn, mast3r, raster  # noqa: F401  (each registers its C signatures)
 from .adam import adamUpdate, adamUpdateBasic  # noqa: F401
 from .cull import lod_cull, lod_select  # noqa: F401
 from .knn import distCUDA2, distIndex2, distIndexQ  # noqa: F401

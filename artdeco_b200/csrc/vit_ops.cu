@@ -1,0 +1,193 @@
+// Memory-bound companions of the tensor-core GEMM on the MASt3R path.  Every kernel that feeds a GEMM writes the
+// bf16 (hi, lo) split of its fp32 result directly (hi = rn(x), lo = rn(x - hi)), so no activation makes an extra
+// fp32 round trip through HBM just to be converted.
+//   layernorm      nn.LayerNorm(eps=1e-6)                 croco/models/croco.py:34, blocks.py:127-130,186-191
+//   rope_heads     RoPE2D (base 100) + head split/transpose   croco/models/pos_embed.py:112-159, curope/kernels.cu:18-82
+//   softmax        attn.softmax(dim=-1)                   blocks.py:106,163
+//   im2col_patch   PatchEmbedDust3R's 16x16/s16 conv as a GEMM operand   dust3r/patch_embed.py:19-29
+//   split          fp32 -> bf16 (hi, lo)
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t i, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// one warp per row, C <= 32*MAXPER
+template <int MAXPER>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(long long rows, int C, const float* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, float* __restrict__ y, __nv_bfloat16* __restrict__ yhi,
+                 __nv_bfloat16* __restrict__ ylo) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * C;
+    float v[MAXPER];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPER; ++k) {
+        const int c = lane + 32 * k;
+        v[k] = c < C ? xr[c] : 0.f;
+        sum += v[k];
+    }
+    sum = adb_warp_sum(sum);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPER; ++k) {
+        const int c = lane + 32 * k;
+        const float d = c < C ? v[k] - mean : 0.f;
+        var += d * d;
+    }
+    var = adb_warp_sum(var) / (float)C;
+    const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int k = 0; k < MAXPER; ++k) {
+        const int c = lane + 32 * k;
+        if (c < C) {
+            const float o = (v[k] - mean) * rstd * gamma[c] + beta[c];
+            const size_t i = (size_t)row * C + c;
+            if (y) y[i] = o;
+            if (yhi) split_store(yhi, ylo, i, o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+split_kernel(long long n, const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        split_store(hi, lo, (size_t)i, x[i]);
+}
+
+// x: fp32 [B, N, ld] (this head group starts at column col0), pos: int64 [B, N, 2] (y, x).
+// mode 0: RoPE, out [B, h, N, 64];  mode 1: no RoPE, out [B, h, N, 64];  mode 2: no RoPE, transposed out [B, h, 64, Npad]
+__global__ void __launch_bounds__(256)
+rope_heads_kernel(int B, int N, int h, long long ld, int col0, const float* __restrict__ x,
+                  const long long* __restrict__ pos, float base, int mode, int Npad, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo) {
+    // one thread per (b, n, head, j<32): handles the pair (j, j+16) of one half when j%32<16 ... simpler: per element
+    const long long total = (long long)B * N * h * 64;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i & 63);
+        const int hh = (int)((i >> 6) % h);
+        const long long bn = (i >> 6) / h;
+        const int n = (int)(bn % N);
+        const int b = (int)(bn / N);
+        const float* xr = x + (size_t)bn * ld + col0 + hh * 64;
+        float v = xr[d];
+        if (mode == 0) {
+            const int half = d >> 5;           // 0: y half, 1: x half
+            const int j = d & 31;              // index inside the half
+            const int jj = j & 15;             // frequency index
+            const float p = (float)pos[(size_t)bn * 2 + half];
+            const float inv_freq = 1.0f / powf(base, (float)jj / 16.0f);
+            const float ang = p * inv_freq;
+            const float c = cosf(ang), s = sinf(ang);
+            const float other = xr[(half << 5) + (j < 16 ? j + 16 : j - 16)];
+            v = j < 16 ? v * c - other * s : v * c + other * s;
+        }
+        size_t o;
+        if (mode == 2) o = (((size_t)b * h + hh) * 64 + d) * Npad + n;
+        else o = (((size_t)b * h + hh) * N + n) * 64 + d;
+        split_store(hi, lo, o, v);
+    }
+}
+
+// one warp per row of length L (row stride ld_in for the fp32 input, ld_out for the bf16 outputs)
+__global__ void __launch_bounds__(256)
+softmax_kernel(long long rows, int L, long long ld_in, long long ld_out, const float* __restrict__ s,
+               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* sr = s + (size_t)row * ld_in;
+    float m = -3.0e38f;
+    for (int c = lane; c < L; c += 32) m = fmaxf(m, sr[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < L; c += 32) sum += expf(sr[c] - m);
+    sum = adb_warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int c = lane; c < L; c += 32) split_store(hi, lo, (size_t)row * ld_out + c, expf(sr[c] - m) * inv);
+}
+
+// img fp32 [B, 3, H, W] -> A [B * (H/16) * (W/16), 768] with column = c*256 + py*16 + px (the conv weight's flattening)
+__global__ void __launch_bounds__(256)
+im2col_patch_kernel(int B, int H, int W, const float* __restrict__ img, __nv_bfloat16* __restrict__ hi,
+                    __nv_bfloat16* __restrict__ lo) {
+    const int gw = W / 16, gh = H / 16;
+    const long long total = (long long)B * gh * gw * 768;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % 768);
+        const long long patch = i / 768;
+        const int pxx = (int)(patch % gw), pyy = (int)((patch / gw) % gh), b = (int)(patch / ((long long)gw * gh));
+        const int c = col >> 8, py = (col >> 4) & 15, px = col & 15;
+        const float v = img[(((size_t)b * 3 + c) * H + (pyy * 16 + py)) * W + pxx * 16 + px];
+        split_store(hi, lo, (size_t)i, v);
+    }
+}
+
+inline int grid_for(long long n) { long long g = (n + 255) / 256; return (int)(g < 148LL * 32 ? g : 148LL * 32); }
+
+}  // namespace
+
+ADB_API int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps,
+                          float* y, void* y_hi, void* y_lo, cudaStream_t stream) {
+    ADB_REQUIRE(rows >= 0 && C >= 1 && C <= 2048, "adb_layernorm: C must be in [1, 2048]");
+    if (rows == 0) return ADB_OK;
+    ADB_REQUIRE(x && gamma && beta && (y || y_hi), "adb_layernorm: null pointer");
+    const int blocks = (int)((rows + 7) / 8);
+    if (C <= 1024)
+        layernorm_kernel<32><<<blocks, 256, 0, stream>>>(rows, C, x, gamma, beta, eps, y, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+    else
+        layernorm_kernel<64><<<blocks, 256, 0, stream>>>(rows, C, x, gamma, beta, eps, y, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+    ADB_CHECK_LAUNCH("layernorm_kernel");
+    return ADB_OK;
+}
+
+ADB_API int adb_split_bf16(long long n, const float* x, void* hi, void* lo, cudaStream_t stream) {
+    ADB_REQUIRE(n >= 0, "adb_split_bf16: bad n");
+    if (n == 0) return ADB_OK;
+    ADB_REQUIRE(x && hi, "adb_split_bf16: null pointer");
+    split_kernel<<<grid_for(n), 256, 0, stream>>>(n, x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    ADB_CHECK_LAUNCH("split_kernel");
+    return ADB_OK;
+}
+
+ADB_API int adb_rope_heads(int B, int N, int h, long long ld, int col0, const float* x, const long long* pos, float base,
+                           int mode, int Npad, void* hi, void* lo, cudaStream_t stream) {
+    ADB_REQUIRE(B >= 0 && N >= 0 && h >= 1 && mode >= 0 && mode <= 2, "adb_rope_heads: bad args");
+    if ((long long)B * N == 0) return ADB_OK;
+    ADB_REQUIRE(x && hi && (mode != 0 || pos), "adb_rope_heads: null pointer");
+    ADB_REQUIRE(mode != 2 || Npad >= N, "adb_rope_heads: Npad < N");
+    rope_heads_kernel<<<grid_for((long long)B * N * h * 64), 256, 0, stream>>>(B, N, h, ld, col0, x, pos, base, mode, Npad,
+                                                                              (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    ADB_CHECK_LAUNCH("rope_heads_kernel");
+    return ADB_OK;
+}
+
+ADB_API int adb_softmax_rows(long long rows, int L, long long ld_in, long long ld_out, const float* s, void* hi, void* lo,
+                             cudaStream_t stream) {
+    ADB_REQUIRE(rows >= 0 && L >= 1, "adb_softmax_rows: bad sizes");
+    if (rows == 0) return ADB_OK;
+    ADB_REQUIRE(s && hi, "adb_softmax_rows: null pointer");
+    softmax_kernel<<<(int)((rows + 7) / 8), 256, 0, stream>>>(rows, L, ld_in, ld_out, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    ADB_CHECK_LAUNCH("softmax_kernel");
+    return ADB_OK;
+}
+
+ADB_API int adb_im2col_patch16(int B, int H, int W, const float* img, void* hi, void* lo, cudaStream_t stream) {
+    ADB_REQUIRE(B >= 0 && H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, "adb_im2col_patch16: H, W must be multiples of 16");
+    if (B == 0) return ADB_OK;
+    ADB_REQUIRE(img && hi, "adb_im2col_patch16: null pointer");
+    im2col_patch_kernel<<<grid_for((long long)B * (H / 16) * (W / 16) * 768), 256, 0, stream>>>(B, H, W, img, (__nv_bfloat16*)hi,
+                                                                                               (__nv_bfloat16*)lo);
+    ADB_CHECK_LAUNCH("im2col_patch_kernel");
+    return ADB_OK;
+}

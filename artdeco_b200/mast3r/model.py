@@ -1,0 +1,321 @@
+"""Host-side mirror of the reference's ``AsymmetricMASt3R`` for inference
+(VSLAM/thirdparty/mast3r/mast3r/model.py:40-68, dust3r/dust3r/model.py:46-211): same constructor defaults as the
+checkpoint ARTDECO loads (ViT-L encoder, 12+12 ViT-B decoder blocks, catmlp+dpt heads, pts3d+desc24), same
+``state_dict`` key names, and the three internals ARTDECO actually drives — ``_encode_image``, ``_decoder``,
+``_downstream_head`` (VSLAM/utils_mast3r.py:30-36,127,132,179) — plus ``forward``.
+
+Every dense contraction of the transformer and of the local-feature MLP runs on the tcgen05 GEMM
+(csrc/gemm_tc.cu) with fused bias/GELU/residual epilogues; LayerNorm, RoPE + head split, softmax and the patch
+im2col are hand-written companion kernels (csrc/vit_ops.cu).  ``precision``:
+  "bf16x3" (default)  three-term split product, fp32-class accuracy (meets the 1e-4 pointmap tolerance)
+  "bf16"              single pass, ~3x less tensor work, ~1e-2 accuracy (NOT within the stated tolerance)
+The DPT convolution stack (croco/models/dpt_block.py) still goes through cuDNN in fp32 in this round — library
+code, flagged in DESIGN.md as the next kernel to write.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+from . import ops
+from .ops import Split
+
+FULL_CFG = dict(enc_embed_dim=1024, enc_depth=24, enc_num_heads=16, dec_embed_dim=768, dec_depth=12, dec_num_heads=12)
+
+
+class _PatchEmbedInfo:
+    def __init__(self, patch_size=16):
+        self.patch_size = (patch_size, patch_size)
+
+
+def _roundup(v, m):
+    return (v + m - 1) // m * m
+
+
+class AsymmetricMASt3R:
+    def __init__(self, precision: str = "bf16x3", **cfg):
+        c = dict(FULL_CFG)
+        c.update({k: v for k, v in cfg.items() if k in FULL_CFG})
+        self.cfg = c
+        for k, v in c.items():
+            setattr(self, k, v)
+        if precision not in ("bf16x3", "bf16"):
+            raise ValueError("precision must be 'bf16x3' or 'bf16'")
+        self.precision = precision
+        self.x3 = precision == "bf16x3"
+        self.patch_embed = _PatchEmbedInfo(16)
+        self.device = torch.device("cpu")
+        self._sd = None          # fp32 tensors (LN params, biases, conv weights)
+        self._w = {}             # name -> Split (bf16 hi/lo GEMM weights)
+        if any(d % 64 for d in (c["enc_embed_dim"] // c["enc_num_heads"], c["dec_embed_dim"] // c["dec_num_heads"])):
+            raise ValueError("head_dim must be 64")
+
+    # ---- nn.Module-like surface the callers use -------------------------------------------------
+    def eval(self):
+        return self
+
+    def share_memory(self):
+        return self
+
+    def to(self, device):
+        self.device = torch.device(device)
+        if self._sd is not None:
+            self._prepare()
+        return self
+
+    def cuda(self, index=0):
+        return self.to(torch.device("cuda", index))
+
+    @classmethod
+    def from_pretrained(cls, path, **kw):
+        """Checkpoint layout of mast3r/model.py:21-37: a dict with 'model' (state dict) and 'args'."""
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        m = cls(**kw)
+        m.load_state_dict(ckpt["model"] if "model" in ckpt else ckpt, strict=False)
+        return m
+
+    def load_state_dict(self, sd, strict: bool = False):
+        sd = dict(sd)
+        if not any(k.startswith("dec_blocks2") for k in sd):   # dust3r/model.py:90-97
+            for k, v in list(sd.items()):
+                if k.startswith("dec_blocks."):
+                    sd[k.replace("dec_blocks.", "dec_blocks2.", 1)] = v
+        self._raw = {k: v.detach().float() for k, v in sd.items()}
+        self._sd = None
+        if self.device.type == "cuda":
+            self._prepare()
+        else:
+            self._sd = {}
+        return self
+
+    def _prepare(self):
+        _lib.require_cuda()
+        dev = self.device
+        raw = self._raw
+        self._sd, self._w = {}, {}
+        for k, v in raw.items():
+            is_gemm_w = (v.dim() == 2 and k.endswith(".weight")) or k == "patch_embed.proj.weight"
+            if is_gemm_w:
+                w2 = v.reshape(v.shape[0], -1).contiguous().to(dev)
+                self._w[k] = ops.split(w2, self.x3)
+            else:
+                self._sd[k] = v.contiguous().to(dev)
+        # fused projk|projv weights for cross attention
+        for blk in ("dec_blocks", "dec_blocks2"):
+            for i in range(self.cfg["dec_depth"]):
+                p = f"{blk}.{i}.cross_attn"
+                if p + ".projk.weight" in raw:
+                    wkv = torch.cat([raw[p + ".projk.weight"], raw[p + ".projv.weight"]], 0).contiguous().to(dev)
+                    self._w[p + ".projkv.weight"] = ops.split(wkv, self.x3)
+                    self._sd[p + ".projkv.bias"] = torch.cat([raw[p + ".projk.bias"], raw[p + ".projv.bias"]]).to(dev)
+
+    # ---- building blocks ------------------------------------------------------------------------
+    def _linear(self, a: Split, name: str, rows: int, **kw):
+        return ops.linear(a, self._w[name + ".weight"], self._sd.get(name + ".bias"), rows, x3=self.x3, **kw)
+
+    def _ln(self, x, name, **kw):
+        return ops.layernorm(x, self._sd[name + ".weight"], self._sd[name + ".bias"], 1e-6, x3=self.x3, **kw)
+
+    def _attn_core(self, q: Split, k: Split, vt: Split, B, h, Nq, Nk, Nkpad) -> Split:
+        dev = q.hi.device
+        s = torch.empty(B * h, Nq, Nk, dtype=torch.float32, device=dev)
+        ops.gemm(q, k, Nq, Nk, 64, batch=B * h, sA=Nq * 64, sB=Nk * 64, out=s, sD=Nq * Nk, alpha=64 ** -0.5)
+        if Nkpad == Nk:
+            p = ops.softmax_rows(s, B * h * Nq, Nk, Nk, x3=self.x3)
+        else:
+            hi = torch.zeros(B * h * Nq, Nkpad, dtype=torch.bfloat16, device=dev)
+            lo = torch.zeros_like(hi) if self.x3 else None
+            _lib.call("adb_softmax_rows", B * h * Nq, Nk, Nk, Nkpad, _lib.ptr(s), _lib.ptr(hi), _lib.ptr(lo), _lib.stream())
+            p = Split(hi, lo)
+        C = h * 64
+        o = Split(torch.empty(B * Nq, C, dtype=torch.bfloat16, device=dev),
+                  torch.empty(B * Nq, C, dtype=torch.bfloat16, device=dev) if self.x3 else None)
+        ops.gemm(p, vt, Nq, 64, Nkpad, batch=B * h, sA=Nq * Nkpad, sB=64 * Nkpad, out_split=o, ldo=C, zdiv=h, sO=64,
+                 sO2=Nq * C)
+        return o
+
+    def _self_attention(self, x, pos, pre, h):
+        """x fp32 [B,N,C] -> x + proj(attn(norm1(x)))  (blocks.py:94-112,128)"""
+        B, N, C = x.shape
+        _, xn = self._ln(x, pre + ".norm1")
+        qkv, _ = self._linear(xn, pre + ".attn.qkv", B * N)
+        Npad = _roundup(N, 8)
+        q = ops.rope_heads(qkv, B, N, h, 3 * C, 0, pos, 0, x3=self.x3)
+        k = ops.rope_heads(qkv, B, N, h, 3 * C, C, pos, 0, x3=self.x3)
+        vt = ops.rope_heads(qkv, B, N, h, 3 * C, 2 * C, None, 2, x3=self.x3, Npad=Npad)
+        o = self._attn_core(q, k, vt, B, h, N, N, Npad)
+        out, _ = self._linear(o, pre + ".attn.proj", B * N, residual=x.reshape(B * N, C))
+        return out.view(B, N, C)
+
+    def _mlp(self, x, norm, pre):
+        B, N, C = x.shape
+        _, xn = self._ln(x, norm)
+        _, hdn = self._linear(xn, pre + ".fc1", B * N, act=1, want_fp32=False, want_split=True)
+        out, _ = self._linear(hdn, pre + ".fc2", B * N, residual=x.reshape(B * N, C))
+        return out.view(B, N, C)
+
+    def _block(self, x, pos, pre, h):
+        x = self._self_attention(x, pos, pre, h)
+        return self._mlp(x, pre + ".norm2", pre + ".mlp")
+
+    def _dec_block(self, x, y, xpos, ypos, pre, h):
+        """DecoderBlock.forward (blocks.py:186-191)."""
+        B, N, C = x.shape
+        Nk = y.shape[1]
+        x = self._self_attention(x, xpos, pre, h)
+        _, yn = self._ln(y, pre + ".norm_y")
+        _, xn = self._ln(x, pre + ".norm2")
+        qf, _ = self._linear(xn, pre + ".cross_attn.projq", B * N)
+        kv, _ = self._linear(yn, pre + ".cross_attn.projkv", B * Nk)
+        Nkpad = _roundup(Nk, 8)
+        q = ops.rope_heads(qf, B, N, h, C, 0, xpos, 0, x3=self.x3)
+        k = ops.rope_heads(kv, B, Nk, h, 2 * C, 0, ypos, 0, x3=self.x3)
+        vt = ops.rope_heads(kv, B, Nk, h, 2 * C, C, None, 2, x3=self.x3, Npad=Nkpad)
+        o = self._attn_core(q, k, vt, B, h, N, Nk, Nkpad)
+        x2, _ = self._linear(o, pre + ".cross_attn.proj", B * N, residual=x.reshape(B * N, C))
+        return self._mlp(x2.view(B, N, C), pre + ".norm3", pre + ".mlp")
+
+    # ---- the reference surface ----------------------------------------------------------------
+    @torch.no_grad()
+    def _encode_image(self, image, true_shape=None):
+        """dust3r/model.py:127-140 -> (x [B,n,E] fp32, pos [B,n,2] int64, None)."""
+        _lib.require_cuda(image)
+        B, _, H, W = image.shape
+        if H % 16 or W % 16:
+            raise AssertionError(f"Input image size ({H}x{W}) is not a multiple of patch size (16).")
+        E = self.cfg["enc_embed_dim"]
+        n = (H // 16) * (W // 16)
+        with torch.cuda.device(image.device):
+            a = ops.im2col_patch16(image.float(), x3=self.x3)
+            x, _ = ops.linear(a, self._w["patch_embed.proj.weight"], self._sd["patch_embed.proj.bias"], B * n, x3=self.x3)
+            x = x.view(B, n, E)
+            yy, xx = torch.arange(H // 16, device=image.device), torch.arange(W // 16, device=image.device)
+            pos = torch.cartesian_prod(yy, xx).view(1, n, 2).expand(B, -1, 2).contiguous()
+            for i in range(self.cfg["enc_depth"]):
+                x = self._block(x, pos, f"enc_blocks.{i}", self.cfg["enc_num_heads"])
+            x, _ = self._ln(x, "enc_norm", want_fp32=True, want_split=False)
+        return x, pos, None
+
+    @torch.no_grad()
+    def _decoder(self, f1, pos1, f2, pos2):
+        """dust3r/model.py:172-191 -> two tuples of 13 tensors (encoder output first, dec_norm'd last)."""
+        B, N1, E = f1.shape
+        N2 = f2.shape[1]
+        Dd, h = self.cfg["dec_embed_dim"], self.cfg["dec_num_heads"]
+        with torch.cuda.device(f1.device):
+            out1, out2 = [f1], [f2]
+            g1, _ = self._linear(ops.split(f1.reshape(B * N1, E), self.x3), "decoder_embed", B * N1)
+            g2, _ = self._linear(ops.split(f2.reshape(B * N2, E), self.x3), "decoder_embed", B * N2)
+            c1, c2 = g1.view(B, N1, Dd), g2.view(B, N2, Dd)
+            for i in range(self.cfg["dec_depth"]):
+                n1 = self._dec_block(c1, c2, pos1, pos2, f"dec_blocks.{i}", h)
+                n2 = self._dec_block(c2, c1, pos2, pos1, f"dec_blocks2.{i}", h)
+                c1, c2 = n1, n2
+                out1.append(c1)
+                out2.append(c2)
+            out1[-1], _ = self._ln(out1[-1], "dec_norm", want_fp32=True, want_split=False)
+            out2[-1], _ = self._ln(out2[-1], "dec_norm", want_fp32=True, want_split=False)
+        return tuple(out1), tuple(out2)
+
+    # DPT (dust3r/heads/dpt_head.py:34-65, croco/models/dpt_block.py) — cuDNN fp32 in this round
+    def _conv(self, x, pre, **kw):
+        return F.conv2d(x, self._sd[pre + ".weight"], self._sd.get(pre + ".bias"), **kw)
+
+    def _rcu(self, x, pre):
+        out = self._conv(F.relu(x), pre + ".conv1", padding=1)
+        return self._conv(F.relu(out), pre + ".conv2", padding=1) + x
+
+    def _fusion(self, pre, x0, x1=None):
+        out = x0 if x1 is None else x0 + self._rcu(x1, pre + ".resConfUnit1")
+        out = self._rcu(out, pre + ".resConfUnit2")
+        out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
+        return self._conv(out, pre + ".out_conv")
+
+    def _dpt(self, pre, decout, H, W):
+        l2 = self.cfg["dec_depth"]
+        hooks = [0, l2 * 2 // 4, l2 * 3 // 4, l2]
+        nh, nw = H // 16, W // 16
+        ly = [decout[k].float().transpose(1, 2).reshape(decout[k].shape[0], -1, nh, nw) for k in hooks]
+        ap, sd = pre + ".act_postprocess", self._sd
+        l0 = F.conv_transpose2d(self._conv(ly[0], ap + ".0.0"), sd[ap + ".0.1.weight"], sd[ap + ".0.1.bias"], stride=4)
+        l1 = F.conv_transpose2d(self._conv(ly[1], ap + ".1.0"), sd[ap + ".1.1.weight"], sd[ap + ".1.1.bias"], stride=2)
+        l2_ = self._conv(ly[2], ap + ".2.0")
+        l3 = self._conv(self._conv(ly[3], ap + ".3.0"), ap + ".3.1", stride=2, padding=1)
+        ls = [F.conv2d(l, sd[f"{pre}.scratch.layer{i + 1}_rn.weight"], None, padding=1) for i, l in enumerate((l0, l1, l2_, l3))]
+        p4 = self._fusion(pre + ".scratch.refinenet4", ls[3])[:, :, :ls[2].shape[2], :ls[2].shape[3]]
+        p3 = self._fusion(pre + ".scratch.refinenet3", p4, ls[2])
+        p2 = self._fusion(pre + ".scratch.refinenet2", p3, ls[1])
+        p1 = self._fusion(pre + ".scratch.refinenet1", p2, ls[0])
+        out = self._conv(p1, pre + ".head.0", padding=1)
+        out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
+        out = F.relu(self._conv(out, pre + ".head.2", padding=1))
+        return self._conv(out, pre + ".head.4")
+
+    @torch.no_grad()
+    def _downstream_head(self, head_num, decout, img_shape, raw: bool = False):
+        """dust3r/model.py:193-197 + mast3r/catmlp_dpt_head.py:71-96.  img_shape: (H, W) or an int tensor [B,2]."""
+        if isinstance(img_shape, torch.Tensor):
+            hw = img_shape.reshape(-1, 2)
+            assert bool((hw == hw[0:1]).all()), "true_shape must be all identical"   # utils/misc.py:56-61
+            H, W = (int(v) for v in hw[0].tolist())
+        else:
+            H, W = int(img_shape[0]), int(img_shape[1])
+        decout = list(decout)
+        pre = f"downstream_head{head_num}"
+        dev = decout[0].device
+        with torch.cuda.device(dev):
+            prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                pts = self._dpt(pre + ".dpt", decout, H, W)
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+            cat = torch.cat([decout[0].float(), decout[-1].float()], -1)
+            B, S, D = cat.shape
+            a = ops.split(cat.reshape(B * S, D), self.x3)
+            _, hdn = self._linear(a, pre + ".head_local_features.fc1", B * S, act=1, want_fp32=False, want_split=True)
+            lf, _ = self._linear(hdn, pre + ".head_local_features.fc2", B * S)
+            lf = F.pixel_shuffle(lf.view(B, S, -1).transpose(-1, -2).reshape(B, -1, H // 16, W // 16), 16)
+            out = torch.cat([pts, lf], 1)
+            if raw:
+                return out
+            fmap = out.permute(0, 2, 3, 1)
+            xyz = fmap[..., 0:3]
+            d = xyz.norm(dim=-1, keepdim=True)
+            res = dict(pts3d=xyz / d.clip(min=1e-8) * torch.expm1(d), conf=1 + fmap[..., 3].exp())
+            desc = fmap[..., 4:28]
+            res["desc"] = desc / desc.norm(dim=-1, keepdim=True)
+            res["desc_conf"] = fmap[..., 28].exp()
+        return res
+
+    @torch.no_grad()
+    def forward(self, view1, view2):
+        """dust3r/model.py:199-211 (symmetrised views are not special-cased: both images are always encoded)."""
+        img1, img2 = view1["img"], view2["img"]
+        B = img1.shape[0]
+        s1 = view1.get("true_shape", torch.tensor(img1.shape[-2:])[None].repeat(B, 1))
+        s2 = view2.get("true_shape", torch.tensor(img2.shape[-2:])[None].repeat(B, 1))
+        if img1.shape[-2:] == img2.shape[-2:]:
+            f, pos, _ = self._encode_image(torch.cat((img1, img2), 0), None)
+            (f1, f2), (p1, p2) = f.chunk(2, 0), pos.chunk(2, 0)
+        else:
+            f1, p1, _ = self._encode_image(img1, s1)
+            f2, p2, _ = self._encode_image(img2, s2)
+        d1, d2 = self._decoder(f1.contiguous(), p1.contiguous(), f2.contiguous(), p2.contiguous())
+        r1 = self._downstream_head(1, [t.float() for t in d1], s1)
+        r2 = self._downstream_head(2, [t.float() for t in d2], s2)
+        r2["pts3d_in_other_view"] = r2.pop("pts3d")
+        return r1, r2
+
+    __call__ = forward
+
+
+def forward_pair(model: AsymmetricMASt3R, img1, img2):
+    """2x _encode_image + _decoder + 2x _downstream_head: the unit BASELINE.json counts as one 'pair' per batch item."""
+    H, W = img1.shape[-2:]
+    f, pos, _ = model._encode_image(torch.cat((img1, img2), 0), None)
+    (f1, f2), (p1, p2) = f.chunk(2, 0), pos.chunk(2, 0)
+    d1, d2 = model._decoder(f1.contiguous(), p1.contiguous(), f2.contiguous(), p2.contiguous())
+    return model._downstream_head(1, d1, (H, W)), model._downstream_head(2, d2, (H, W))

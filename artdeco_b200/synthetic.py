@@ -48,3 +48,34 @@ def upstream_grads(width: int, height: int, seed: int = 1, C: int = 1):
 def ssim_pair(B=1, CH=3, H=1080, W=1920, seed=0):
     g = torch.Generator().manual_seed(seed)
     return torch.rand(B, CH, H, W, generator=g), torch.rand(B, CH, H, W, generator=g)
+
+
+def det_weights(shapes: dict, seed: int = 0, device="cpu"):
+    """Deterministic per-tensor weights for a {name: shape} table (no checkpoint is available offline): each tensor is
+    drawn from its own generator seeded by crc32(name), so any implementation that knows the names and shapes gets
+    bit-identical values regardless of construction order.  Scales keep activations O(1) through 36 layers:
+    matrices/convs ~ N(0, 1/fan_in), LayerNorm weights 1 + 0.1 N(0,1), biases 0.02 N(0,1)."""
+    import zlib
+    out = {}
+    for name, shape in shapes.items():
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) & 0x7fffffff)
+        t = torch.randn(*shape, generator=g, dtype=torch.float32)
+        if len(shape) == 1:
+            is_norm_w = name.endswith(".weight")
+            t = 1.0 + 0.1 * t if is_norm_w else 0.02 * t
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            if ".act_postprocess." in name and name.endswith(".1.weight") and len(shape) == 4 and shape[0] == shape[1] and shape[2] in (2, 4):
+                fan_in = shape[0]          # ConvTranspose2d: [in, out, k, k], each output pixel sees `in` taps
+            t = t * (1.0 / fan_in) ** 0.5
+            if name.endswith(".dpt.head.4.weight") or name.endswith(".head_local_features.fc2.weight"):
+                t = t * 0.3                # keeps |log-depth| ~2 like a metric checkpoint (expm1 amplifies errors by e^d)
+        out[name] = t.to(device)
+    return out
+
+
+def mast3r_pair(B: int = 1, H: int = 512, W: int = 512, seed: int = 0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(B, 3, H, W, generator=g) * 2 - 1, torch.rand(B, 3, H, W, generator=g) * 2 - 1)

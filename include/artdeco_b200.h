@@ -98,6 +98,32 @@ int adb_knn_index(long long P, const float* points, int K, long long Q, const in
                   const unsigned char* candidate /*[P] or NULL*/, float* dists /*[Q*K]*/, int32_t* ids /*[Q*K]*/,
                   void* ws, size_t ws_bytes, adb_stream_t stream);
 
+/* ---- MASt3R: tensor-core GEMM (tcgen05 + TMA) and its companions ----
+ * adb_gemm_bf16 replaces every nn.Linear / q@k^T / attn@v of the reference model
+ *   (VSLAM/thirdparty/mast3r/dust3r/croco/models/blocks.py:58-112,140-169; dust3r/dust3r/patch_embed.py:19-29;
+ *    mast3r/catmlp_dpt_head.py:67-69): D[z] = act(alpha * A[z] * B[z]^T + bias) + residual[z],
+ *   A bf16 [batch][M][K], B bf16 [batch][N][K], both K-contiguous; *_lo != NULL selects the 3-term bf16x3 product;
+ *   outputs fp32 D and/or a bf16 (hi, lo) split; output offset = (z / zdiv) * s?2 + (z % zdiv) * s? (zdiv <= 0: z * s?).
+ * adb_layernorm     nn.LayerNorm(eps) rows of C (croco.py:34, blocks.py:127-130,186-191)
+ * adb_rope_heads    RoPE2D + head split (pos_embed.py:112-159 / curope/kernels.cu:18-82): x fp32 [B,N,ld] -> bf16 split
+ *                   [B,h,N,64] (mode 0 RoPE, 1 plain) or transposed [B,h,64,Npad] (mode 2)
+ * adb_softmax_rows  attn.softmax(-1) (blocks.py:106,163), fp32 in, bf16 split out
+ * adb_im2col_patch16  operand of the 16x16/s16 patch-embedding conv as a GEMM (patch_embed.py:19-29)
+ * adb_split_bf16    x -> (hi = rn(x), lo = rn(x - hi)) */
+int adb_gemm_bf16(int batch, int M, int N, int K, const void* A_hi, const void* A_lo, long long lda, long long sA,
+                  const void* B_hi, const void* B_lo, long long ldb, long long sB, float* D, long long ldd, long long sD,
+                  void* D_hi, void* D_lo, long long ldo, long long sO, const float* bias, const float* residual,
+                  long long ldr, long long sR, float alpha, int act /*0 none, 1 GELU(erf)*/, int zdiv, long long sD2,
+                  long long sO2, long long sR2, adb_stream_t stream);
+int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
+                  void* y_hi, void* y_lo, adb_stream_t stream);
+int adb_split_bf16(long long n, const float* x, void* hi, void* lo, adb_stream_t stream);
+int adb_rope_heads(int B, int N, int h, long long ld, int col0, const float* x, const long long* pos /*[B,N,2] (y,x)*/,
+                   float base, int mode, int Npad, void* hi, void* lo, adb_stream_t stream);
+int adb_softmax_rows(long long rows, int L, long long ld_in, long long ld_out, const float* s, void* hi, void* lo,
+                     adb_stream_t stream);
+int adb_im2col_patch16(int B, int H, int W, const float* img, void* hi, void* lo, adb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

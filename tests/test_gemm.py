@@ -1,0 +1,92 @@
+"""tcgen05 GEMM + ViT companion kernels against plain PyTorch fp64 references (floating-point kernels: the torch
+reference is the oracle here, per the tier rules)."""
+import pytest
+import torch
+
+from helpers import rel_err
+
+
+def _mk(shape, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g).to(dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 128), (1024, 3072, 1024), (1000, 200, 136), (77, 64, 1024)])
+def test_gemm_bf16x3_matches_fp64(cuda, M, N, K):
+    from artdeco_b200.mast3r import ops
+    a, w = _mk((M, K), 1, cuda), _mk((N, K), 2, cuda) * 0.05
+    bias, res = _mk((N,), 3, cuda), _mk((M, N), 4, cuda)
+    ref = a.double() @ w.double().T
+    out = torch.empty(M, N, device=cuda)
+    ops.gemm(ops.split(a), ops.split(w), M, N, K, out=out)
+    assert rel_err(out, ref) < 2e-5, "bf16x3 product must be fp32-class (north-star 1e-4 budget over 36 layers)"
+    # fused epilogue: alpha, bias, exact GELU, residual, split output
+    sp = ops.Split(torch.empty(M, N, dtype=torch.bfloat16, device=cuda), torch.empty(M, N, dtype=torch.bfloat16, device=cuda))
+    ops.gemm(ops.split(a), ops.split(w), M, N, K, out=out, out_split=sp, bias=bias, residual=res, alpha=0.5, act=1)
+    ref2 = torch.nn.functional.gelu(0.5 * ref + bias.double()) + res.double()
+    assert rel_err(out, ref2) < 2e-5
+    assert rel_err(sp.hi.float() + sp.lo.float(), out) < 2e-5   # hi+lo keeps 16 mantissa bits
+    # single-pass bf16 (the fast mode) is only bf16-accurate
+    ops.gemm(ops.split(a, x3=False), ops.split(w, x3=False), M, N, K, out=out)
+    e1 = rel_err(out, ref)
+    assert 1e-4 < e1 < 2e-2
+
+
+@pytest.mark.gpu
+def test_gemm_batched_with_head_addressing(cuda):
+    """The attention pattern: batch = B*h, outputs written straight into [B, N, h*64]."""
+    from artdeco_b200.mast3r import ops
+    B, h, N = 2, 3, 200
+    q, k = _mk((B, h, N, 64), 1, cuda), _mk((B, h, N, 64), 2, cuda)
+    s = torch.empty(B * h, N, N, device=cuda)
+    ops.gemm(ops.split(q), ops.split(k), N, N, 64, batch=B * h, sA=N * 64, sB=N * 64, out=s, sD=N * N, alpha=0.125)
+    assert rel_err(s.view(B, h, N, N), 0.125 * q.double() @ k.double().transpose(-1, -2)) < 2e-5
+    p = torch.softmax(s, -1)
+    v = _mk((B, h, N, 64), 3, cuda)
+    Npad = 208
+    vt = torch.zeros(B, h, 64, Npad, device=cuda)
+    vt[..., :N] = v.transpose(-1, -2)
+    pp = torch.zeros(B * h, N, Npad, device=cuda)
+    pp[..., :N] = p
+    o = torch.empty(B, N, h * 64, device=cuda)
+    ops.gemm(ops.split(pp), ops.split(vt), N, 64, Npad, batch=B * h, sA=N * Npad, sB=64 * Npad, out=o, ldd=h * 64,
+             zdiv=h, sD=64, sD2=N * h * 64)
+    ref = (p.view(B, h, N, N).double() @ v.double()).permute(0, 2, 1, 3).reshape(B, N, h * 64)
+    assert rel_err(o, ref) < 2e-5
+
+
+@pytest.mark.gpu
+def test_layernorm_softmax_rope_im2col(cuda):
+    from artdeco_b200.mast3r import ops
+    x = _mk((3, 50, 768), 5, cuda)
+    g, b = _mk((768,), 6, cuda), _mk((768,), 7, cuda)
+    y, sp = ops.layernorm(x, g, b, want_fp32=True)
+    ref = torch.nn.functional.layer_norm(x.double(), (768,), g.double(), b.double(), 1e-6)
+    assert rel_err(y, ref) < 1e-5 and rel_err(sp.hi.float() + sp.lo.float(), ref) < 2e-5
+    s = _mk((40, 300), 8, cuda) * 3
+    p = ops.softmax_rows(s, 40, 300, 300)
+    assert rel_err(p.hi.float() + p.lo.float(), torch.softmax(s.double(), -1)) < 2e-5
+    # RoPE2D against the reference formula (croco/models/pos_embed.py:112-159)
+    B, N, h = 2, 48, 4
+    qkv = _mk((B, N, 3 * h * 64), 9, cuda)
+    pos = torch.cartesian_prod(torch.arange(6), torch.arange(8))[None].expand(B, -1, 2).contiguous().to(cuda)
+    q = ops.rope_heads(qkv, B, N, h, 3 * h * 64, 0, pos, 0)
+    tok = qkv.view(B, N, 3, h, 64)[:, :, 0].permute(0, 2, 1, 3).double()   # B,h,N,64
+
+    def rope1d(t, p1):
+        D = 32
+        inv = 1.0 / (100.0 ** (torch.arange(0, D, 2, dtype=torch.float64, device=cuda) / D))
+        fr = p1[..., None].double() * inv
+        fr = torch.cat([fr, fr], -1)[:, None]
+        rot = torch.cat([-t[..., 16:], t[..., :16]], -1)
+        return t * fr.cos() + rot * fr.sin()
+    ref = torch.cat([rope1d(tok[..., :32], pos[..., 0]), rope1d(tok[..., 32:], pos[..., 1])], -1)
+    assert rel_err(q.hi.float() + q.lo.float(), ref) < 2e-5
+    vt = ops.rope_heads(qkv, B, N, h, 3 * h * 64, 2 * h * 64, None, 2)
+    refv = qkv.view(B, N, 3, h, 64)[:, :, 2].permute(0, 2, 3, 1)
+    assert rel_err(vt.hi.float() + vt.lo.float(), refv) < 1e-5
+    img = _mk((2, 3, 32, 48), 10, cuda)
+    a = ops.im2col_patch16(img)
+    refa = torch.nn.functional.unfold(img, 16, stride=16).transpose(1, 2).reshape(-1, 768)
+    assert rel_err(a.hi.float() + a.lo.float(), refa) < 1e-5

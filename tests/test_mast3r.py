@@ -1,0 +1,126 @@
+"""MASt3R: oracle restatement vs committed goldens (CPU), CUDA model vs goldens and vs the oracle (GPU).
+
+Goldens (tests/golden/mast3r_small.pt, mast3r_full.pt) were produced by running the REAL reference module in the build
+container on deterministic weights (tests/golden/make_mast3r_golden.py); weights are regenerated here from the same
+recipe (synthetic.det_weights), so nothing but a few hundred KB of outputs is committed.
+Tolerance: 1e-4 of each tensor's scale (BASELINE.json: "within 1e-4 relative fp32 for ... pointmaps")."""
+import pathlib
+
+import pytest
+import torch
+
+from artdeco_b200 import synthetic
+from helpers import rel_err
+from oracle import mast3r_torch as mt
+
+GOLD = pathlib.Path(__file__).parent / "golden"
+KEYS = ("pts3d", "conf", "desc", "desc_conf")
+
+
+def _gold(tag):
+    p = GOLD / f"mast3r_{tag}.pt"
+    if not p.exists():
+        pytest.skip(f"{p.name} not generated")
+    return torch.load(p, weights_only=False)
+
+
+def test_oracle_matches_reference_golden_small():
+    g = _gold("small")
+    cfg, H, W = g["cfg"], g["H"], g["W"]
+    sd = synthetic.det_weights(mt.param_shapes(cfg))
+    img1, img2 = synthetic.mast3r_pair(1, H, W, seed=0)
+    with torch.inference_mode():
+        f1, p1 = mt.encode_image(sd, cfg, img1)
+        f2, p2 = mt.encode_image(sd, cfg, img2)
+        d1, d2 = mt.decoder(sd, cfg, f1, p1, f2, p2)
+        o1 = mt.downstream_head(sd, cfg, 1, d1, H, W)
+        o2 = mt.downstream_head(sd, cfg, 2, d2, H, W)
+    assert rel_err(f1, g["enc1"]) < 1e-5 and rel_err(d1[-1], g["dec1_last"]) < 1e-5 and rel_err(d2[6], g["dec2_mid"]) < 1e-5
+    for k in KEYS:
+        assert rel_err(o1[k], g["h1." + k]) < 3e-5, k
+        assert rel_err(o2[k], g["h2." + k]) < 3e-5, k
+
+
+def test_det_weights_are_order_independent():
+    s = mt.param_shapes(mt.SMALL_CFG)
+    a = synthetic.det_weights(s)
+    b = synthetic.det_weights(dict(reversed(list(s.items()))))
+    assert all(torch.equal(a[k], b[k]) for k in s) and len(s) > 400
+
+
+def _run_cuda(cfg, H, W, dev, precision="bf16x3"):
+    from artdeco_b200.mast3r import AsymmetricMASt3R
+    sd = synthetic.det_weights(mt.param_shapes(cfg))
+    m = AsymmetricMASt3R(precision=precision, **cfg)
+    m.load_state_dict(sd)
+    m.to(dev)
+    img1, img2 = synthetic.mast3r_pair(1, H, W, seed=0)
+    shape = torch.tensor([[H, W]])
+    f1, p1, _ = m._encode_image(img1.to(dev), shape)
+    f2, p2, _ = m._encode_image(img2.to(dev), shape)
+    d1, d2 = m._decoder(f1, p1, f2, p2)
+    r1 = m._downstream_head(1, [t.float() for t in d1], shape)
+    r2 = m._downstream_head(2, [t.float() for t in d2], shape.to(dev))      # on-device shape as at utils_mast3r.py:177
+    return m, sd, (f1, p1, d1, d2, r1, r2)
+
+
+@pytest.mark.gpu
+def test_cuda_model_matches_reference_golden_small(cuda):
+    g = _gold("small")
+    m, sd, (f1, p1, d1, d2, r1, r2) = _run_cuda(g["cfg"], g["H"], g["W"], cuda)
+    assert len(d1) == 13 and d1[0].shape[-1] == g["cfg"]["enc_embed_dim"] and p1.dtype == torch.int64
+    assert rel_err(f1, g["enc1"]) < 1e-4, "encoder tokens"
+    assert rel_err(d1[-1], g["dec1_last"]) < 1e-4 and rel_err(d2[6], g["dec2_mid"]) < 1e-4, "decoder tokens"
+    for k in KEYS:
+        assert rel_err(r1[k], g["h1." + k]) < 1e-4, f"head1 {k}"
+        assert rel_err(r2[k], g["h2." + k]) < 1e-4, f"head2 {k}"
+    # forward(): the named surface (dust3r/model.py:199-211)
+    img1, img2 = synthetic.mast3r_pair(1, g["H"], g["W"], seed=0)
+    o1, o2 = m.forward({"img": img1.to(cuda)}, {"img": img2.to(cuda)})
+    assert "pts3d_in_other_view" in o2 and "pts3d" not in o2
+    assert rel_err(o1["pts3d"], g["h1.pts3d"]) < 1e-4 and rel_err(o2["pts3d_in_other_view"], g["h2.pts3d"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_model_matches_reference_golden_full(cuda):
+    """ViT-L/ViT-B at 512x512 (the BASELINE configuration) against strided samples of the real reference's outputs."""
+    g = _gold("full")
+    s = g["stride"]
+    m, sd, (f1, p1, d1, d2, r1, r2) = _run_cuda(g["cfg"], g["H"], g["W"], cuda)
+    assert f1.shape == (1, 1024, 1024)
+    assert rel_err(f1[:, ::s], g["enc1"]) < 1e-4
+    assert rel_err(d1[-1][:, ::s], g["dec1_last"]) < 1e-4 and rel_err(d2[6][:, ::s], g["dec2_mid"]) < 1e-4
+    for k in KEYS:
+        assert rel_err(r1[k][:, ::s, ::s], g["h1." + k]) < 1e-4, f"head1 {k}"
+        assert rel_err(r2[k][:, ::s, ::s], g["h2." + k]) < 1e-4, f"head2 {k}"
+
+
+@pytest.mark.gpu
+def test_cuda_model_vs_oracle_odd_shape_and_batch(cuda):
+    """512x384-style aspect (PINGPONG's real shape, scaled down) and batch 2, against the oracle run on the GPU in fp32."""
+    cfg, H, W = mt.SMALL_CFG, 96, 128
+    from artdeco_b200.mast3r import AsymmetricMASt3R
+    sd = synthetic.det_weights(mt.param_shapes(cfg))
+    m = AsymmetricMASt3R(**cfg).load_state_dict(sd).to(cuda)
+    img1, img2 = synthetic.mast3r_pair(2, H, W, seed=3)
+    sdg = {k: v.to(cuda) for k, v in sd.items()}
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.inference_mode():
+            a1, a2 = mt.forward_pair(sdg, cfg, img1.to(cuda), img2.to(cuda))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    from artdeco_b200.mast3r import forward_pair
+    b1, b2 = forward_pair(m, img1.to(cuda), img2.to(cuda))
+    for k in KEYS:
+        assert rel_err(b1[k], a1[k]) < 1e-4 and rel_err(b2[k], a2[k]) < 1e-4, k
+
+
+@pytest.mark.gpu
+def test_single_pass_bf16_is_outside_tolerance(cuda):
+    """Documents why bf16x3 is the default: one bf16 pass misses the 1e-4 contract by two orders of magnitude."""
+    g = _gold("small")
+    _, _, (f1, *_rest) = _run_cuda(g["cfg"], g["H"], g["W"], cuda, precision="bf16")
+    e = rel_err(f1, g["enc1"])
+    assert 1e-4 < e < 0.2
