@@ -64,37 +64,93 @@ split_kernel(long long n, const float* __restrict__ x, __nv_bfloat16* __restrict
         split_store(hi, lo, (size_t)i, x[i]);
 }
 
-// x: fp32 [B, N, ld] (this head group starts at column col0), pos: int64 [B, N, 2] (y, x).
-// mode 0: RoPE, out [B, h, N, 64];  mode 1: no RoPE, out [B, h, N, 64];  mode 2: no RoPE, transposed out [B, h, 64, Npad]
+// x: fp32 [B, N, ld] (this head group starts at column col0), pos: int64 [B, N, 2] (y, x),
+// table: float2 [n_pos][16] = (cos, sin)(p * base^(-j/16)) computed by the caller exactly as the reference does
+// (pos_embed.py:118-127).  mode 0: RoPE, mode 1: plain; out [B, h, N, 64].  One thread per 8 consecutive dims.
 __global__ void __launch_bounds__(256)
 rope_heads_kernel(int B, int N, int h, long long ld, int col0, const float* __restrict__ x,
-                  const long long* __restrict__ pos, float base, int mode, int Npad, __nv_bfloat16* __restrict__ hi,
-                  __nv_bfloat16* __restrict__ lo) {
-    // one thread per (b, n, head, j<32): handles the pair (j, j+16) of one half when j%32<16 ... simpler: per element
-    const long long total = (long long)B * N * h * 64;
+                  const long long* __restrict__ pos, const float2* __restrict__ table, int n_pos, int mode,
+                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const long long total = (long long)B * N * h * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int d = (int)(i & 63);
-        const int hh = (int)((i >> 6) % h);
-        const long long bn = (i >> 6) / h;
+        const int d0 = (int)(i & 7) * 8;
+        const int hh = (int)((i >> 3) % h);
+        const long long bn = (i >> 3) / h;
         const int n = (int)(bn % N);
         const int b = (int)(bn / N);
         const float* xr = x + (size_t)bn * ld + col0 + hh * 64;
-        float v = xr[d];
-        if (mode == 0) {
-            const int half = d >> 5;           // 0: y half, 1: x half
-            const int j = d & 31;              // index inside the half
-            const int jj = j & 15;             // frequency index
-            const float p = (float)pos[(size_t)bn * 2 + half];
-            const float inv_freq = 1.0f / powf(base, (float)jj / 16.0f);
-            const float ang = p * inv_freq;
-            const float c = cosf(ang), s = sinf(ang);
-            const float other = xr[(half << 5) + (j < 16 ? j + 16 : j - 16)];
-            v = j < 16 ? v * c - other * s : v * c + other * s;
+        float v[8];
+        {
+            const float4 a = *reinterpret_cast<const float4*>(xr + d0), c = *reinterpret_cast<const float4*>(xr + d0 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
         }
-        size_t o;
-        if (mode == 2) o = (((size_t)b * h + hh) * 64 + d) * Npad + n;
-        else o = (((size_t)b * h + hh) * N + n) * 64 + d;
-        split_store(hi, lo, o, v);
+        if (mode == 0) {
+            const int half = d0 >> 5, j0 = d0 & 31, jj0 = j0 & 15;
+            const bool first = j0 < 16;
+            const float* xp = xr + (half << 5) + (first ? j0 + 16 : j0 - 16);
+            const float4 a = *reinterpret_cast<const float4*>(xp), c = *reinterpret_cast<const float4*>(xp + 4);
+            const float o[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+            long long pz = pos[(size_t)bn * 2 + half];
+            pz = pz < 0 ? 0 : (pz >= n_pos ? n_pos - 1 : pz);
+            const float2* tb = table + (size_t)pz * 16 + jj0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float2 cs = __ldg(tb + e);
+                v[e] = first ? v[e] * cs.x - o[e] * cs.y : v[e] * cs.x + o[e] * cs.y;
+            }
+        }
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat16 ah = __float2bfloat16_rn(v[2 * e]), bh = __float2bfloat16_rn(v[2 * e + 1]);
+            const __nv_bfloat16 al = __float2bfloat16_rn(v[2 * e] - __bfloat162float(ah));
+            const __nv_bfloat16 bl = __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(bh));
+            hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+            lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+        }
+        const size_t o8 = (((size_t)b * h + hh) * N + n) * 64 + d0;
+        *reinterpret_cast<uint4*>(hi + o8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (lo) *reinterpret_cast<uint4*>(lo + o8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+}
+
+// mode 2: plain values, transposed output [B, h, 64, Npad] through a shared-memory tile (coalesced on both sides).
+// grid = (ceil(N/64), h, B), block = 256.
+__global__ void __launch_bounds__(256)
+heads_transpose_kernel(int N, int h, long long ld, int col0, const float* __restrict__ x, int Npad,
+                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    __shared__ float tile[64][65];
+    const int n0 = blockIdx.x * 64, hh = blockIdx.y, b = blockIdx.z;
+    const int t = threadIdx.x;
+    {
+        const int tok = t >> 2, dq = (t & 3) * 16;
+        const int n = n0 + tok;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < N) q = *reinterpret_cast<const float4*>(x + ((size_t)b * N + n) * ld + col0 + hh * 64 + dq + 4 * e);
+            tile[dq + 4 * e][tok] = q.x; tile[dq + 4 * e + 1][tok] = q.y; tile[dq + 4 * e + 2][tok] = q.z; tile[dq + 4 * e + 3][tok] = q.w;
+        }
+    }
+    __syncthreads();
+    const int d = t >> 2, tq = (t & 3) * 16;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int n = n0 + tq + 8 * g;
+        if (n >= Npad) continue;          // Npad is a multiple of 8, so an 8-token group never straddles it
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float f0 = tile[d][tq + 8 * g + 2 * e], f1 = tile[d][tq + 8 * g + 2 * e + 1];
+            const __nv_bfloat16 ah = __float2bfloat16_rn(f0), bh = __float2bfloat16_rn(f1);
+            const __nv_bfloat16 al = __float2bfloat16_rn(f0 - __bfloat162float(ah));
+            const __nv_bfloat16 bl = __float2bfloat16_rn(f1 - __bfloat162float(bh));
+            hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+            lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+        }
+        const size_t o = (((size_t)b * h + hh) * 64 + d) * Npad + n;
+        *reinterpret_cast<uint4*>(hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
 }
 
@@ -160,14 +216,22 @@ ADB_API int adb_split_bf16(long long n, const float* x, void* hi, void* lo, cuda
     return ADB_OK;
 }
 
-ADB_API int adb_rope_heads(int B, int N, int h, long long ld, int col0, const float* x, const long long* pos, float base,
-                           int mode, int Npad, void* hi, void* lo, cudaStream_t stream) {
+ADB_API int adb_rope_heads(int B, int N, int h, long long ld, int col0, const float* x, const long long* pos,
+                           const float* table, int n_pos, int mode, int Npad, void* hi, void* lo, cudaStream_t stream) {
     ADB_REQUIRE(B >= 0 && N >= 0 && h >= 1 && mode >= 0 && mode <= 2, "adb_rope_heads: bad args");
     if ((long long)B * N == 0) return ADB_OK;
-    ADB_REQUIRE(x && hi && (mode != 0 || pos), "adb_rope_heads: null pointer");
-    ADB_REQUIRE(mode != 2 || Npad >= N, "adb_rope_heads: Npad < N");
-    rope_heads_kernel<<<grid_for((long long)B * N * h * 64), 256, 0, stream>>>(B, N, h, ld, col0, x, pos, base, mode, Npad,
-                                                                              (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    ADB_REQUIRE(x && hi && (mode != 0 || (pos && table && n_pos > 0)), "adb_rope_heads: null pointer");
+    ADB_REQUIRE(ld % 4 == 0 && col0 % 4 == 0 && ((uintptr_t)x % 16 == 0), "adb_rope_heads: x must allow 128-bit loads");
+    if (mode == 2) {
+        ADB_REQUIRE(Npad >= N && Npad % 8 == 0, "adb_rope_heads: Npad must be a multiple of 8 and >= N");
+        dim3 grid(adb_cdiv(Npad, 64), h, B);
+        heads_transpose_kernel<<<grid, 256, 0, stream>>>(N, h, ld, col0, x, Npad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+        ADB_CHECK_LAUNCH("heads_transpose_kernel");
+        return ADB_OK;
+    }
+    rope_heads_kernel<<<grid_for((long long)B * N * h * 8), 256, 0, stream>>>(B, N, h, ld, col0, x, pos,
+                                                                             (const float2*)table, n_pos, mode,
+                                                                             (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
     ADB_CHECK_LAUNCH("rope_heads_kernel");
     return ADB_OK;
 }

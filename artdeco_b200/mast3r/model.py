@@ -9,8 +9,8 @@ Every dense contraction of the transformer and of the local-feature MLP runs on 
 im2col are hand-written companion kernels (csrc/vit_ops.cu).  ``precision``:
   "bf16x3" (default)  three-term split product, fp32-class accuracy (meets the 1e-4 pointmap tolerance)
   "bf16"              single pass, ~3x less tensor work, ~1e-2 accuracy (NOT within the stated tolerance)
-The DPT convolution stack (croco/models/dpt_block.py) still goes through cuDNN in fp32 in this round — library
-code, flagged in DESIGN.md as the next kernel to write.
+The DPT convolution stack (croco/models/dpt_block.py) runs on the same kernel in its implicit-GEMM conv mode (NHWC
+activations, 4-D TMA boxes); torch is left with the bilinear upsampling and a few reshapes.
 """
 from __future__ import annotations
 
@@ -99,6 +99,15 @@ class AsymmetricMASt3R:
             if is_gemm_w:
                 w2 = v.reshape(v.shape[0], -1).contiguous().to(dev)
                 self._w[k] = ops.split(w2, self.x3)
+            elif v.dim() == 4 and ".dpt." in k and k.endswith(".weight"):
+                if ".act_postprocess." in k and k.endswith(".1.weight") and v.shape[-1] in (2, 4):
+                    # ConvTranspose2d [Cin, Cout, k, k] -> linear weight [(co, i, j), ci]
+                    wt = v.to(dev).permute(1, 2, 3, 0).reshape(-1, v.shape[0]).contiguous()
+                    self._w[k] = ops.split(wt, self.x3)
+                elif v.shape[-1] == 3:
+                    self._w[k] = ops.prep_conv3x3_weight(v.to(dev), self.x3)
+                else:  # 1x1
+                    self._w[k] = ops.split(v.to(dev).reshape(v.shape[0], v.shape[1]).contiguous(), self.x3)
             else:
                 self._sd[k] = v.contiguous().to(dev)
         # fused projk|projv weights for cross attention
@@ -218,39 +227,85 @@ class AsymmetricMASt3R:
             out2[-1], _ = self._ln(out2[-1], "dec_norm", want_fp32=True, want_split=False)
         return tuple(out1), tuple(out2)
 
-    # DPT (dust3r/heads/dpt_head.py:34-65, croco/models/dpt_block.py) — cuDNN fp32 in this round
-    def _conv(self, x, pre, **kw):
-        return F.conv2d(x, self._sd[pre + ".weight"], self._sd.get(pre + ".bias"), **kw)
+    # ---- DPT head (dust3r/heads/dpt_head.py:34-65, croco/models/dpt_block.py:79-218,356-410) ----------------
+    # All 3x3 / 1x1 convolutions and both ConvTranspose layers run on the tcgen05 kernel (implicit GEMM over NHWC
+    # activations); only the bilinear x2 upsampling (align_corners=True) and pixel rearrangements stay in torch.
+    def _c3(self, x: Split, B, H, W, name, **kw):
+        w = self._w[name + ".weight"]
+        cin = x.hi.shape[-1]
+        return ops.conv3x3(x, B, H, W, cin, w, self._sd.get(name + ".bias"), w.hi.shape[0], x3=self.x3, **kw)
 
-    def _rcu(self, x, pre):
-        out = self._conv(F.relu(x), pre + ".conv1", padding=1)
-        return self._conv(F.relu(out), pre + ".conv2", padding=1) + x
+    def _c1(self, x: Split, rows, name, **kw):
+        return ops.linear(x, self._w[name + ".weight"], self._sd.get(name + ".bias"), rows, x3=self.x3, **kw)
 
-    def _fusion(self, pre, x0, x1=None):
-        out = x0 if x1 is None else x0 + self._rcu(x1, pre + ".resConfUnit1")
-        out = self._rcu(out, pre + ".resConfUnit2")
-        out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
-        return self._conv(out, pre + ".out_conv")
+    @staticmethod
+    def _up2(x_nhwc):
+        y = F.interpolate(x_nhwc.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+        return y.permute(0, 2, 3, 1).contiguous()
+
+    def _rcu(self, x_f32, x_relu: Split, B, H, W, pre, extra_residual=None, out_fp32=True, out_relu_split=False,
+             out_plain_split=False):
+        """ResidualConvUnit: conv2(relu(conv1(relu(x)))) + x (+ extra_residual)."""
+        _, h = self._c3(x_relu, B, H, W, pre + ".conv1", act=2, want_fp32=False, want_split=True)
+        res = x_f32 if extra_residual is None else x_f32 + extra_residual
+        return self._c3(h, B, H, W, pre + ".conv2", residual=res.contiguous(), want_fp32=out_fp32,
+                        want_split=out_relu_split or out_plain_split, split_relu=out_relu_split)
+
+    def _fusion(self, pre, B, H, W, x0_f32, x0_relu: Split = None, x1=None):
+        """FeatureFusionBlock: [x0 + RCU1(x1)] -> RCU2 -> up x2 -> out_conv (the 1x1 commutes with the bilinear
+        upsampling, so it is applied at the low resolution: a quarter of the FLOPs, same result)."""
+        if x1 is not None:
+            x1_f32, x1_relu = x1
+            x0_f32, x0_relu = self._rcu(x1_f32, x1_relu, B, H, W, pre + ".resConfUnit1", extra_residual=x0_f32,
+                                        out_relu_split=True)
+        _, o = self._rcu(x0_f32, x0_relu, B, H, W, pre + ".resConfUnit2", out_fp32=False, out_plain_split=True)
+        y, _ = self._c1(Split(o.hi.view(B * H * W, -1), o.lo.view(B * H * W, -1) if o.lo is not None else None),
+                        B * H * W, pre + ".out_conv")
+        return self._up2(y.view(B, H, W, -1))
 
     def _dpt(self, pre, decout, H, W):
         l2 = self.cfg["dec_depth"]
         hooks = [0, l2 * 2 // 4, l2 * 3 // 4, l2]
         nh, nw = H // 16, W // 16
-        ly = [decout[k].float().transpose(1, 2).reshape(decout[k].shape[0], -1, nh, nw) for k in hooks]
-        ap, sd = pre + ".act_postprocess", self._sd
-        l0 = F.conv_transpose2d(self._conv(ly[0], ap + ".0.0"), sd[ap + ".0.1.weight"], sd[ap + ".0.1.bias"], stride=4)
-        l1 = F.conv_transpose2d(self._conv(ly[1], ap + ".1.0"), sd[ap + ".1.1.weight"], sd[ap + ".1.1.bias"], stride=2)
-        l2_ = self._conv(ly[2], ap + ".2.0")
-        l3 = self._conv(self._conv(ly[3], ap + ".3.0"), ap + ".3.1", stride=2, padding=1)
-        ls = [F.conv2d(l, sd[f"{pre}.scratch.layer{i + 1}_rn.weight"], None, padding=1) for i, l in enumerate((l0, l1, l2_, l3))]
-        p4 = self._fusion(pre + ".scratch.refinenet4", ls[3])[:, :, :ls[2].shape[2], :ls[2].shape[3]]
-        p3 = self._fusion(pre + ".scratch.refinenet3", p4, ls[2])
-        p2 = self._fusion(pre + ".scratch.refinenet2", p3, ls[1])
-        p1 = self._fusion(pre + ".scratch.refinenet1", p2, ls[0])
-        out = self._conv(p1, pre + ".head.0", padding=1)
-        out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
-        out = F.relu(self._conv(out, pre + ".head.2", padding=1))
-        return self._conv(out, pre + ".head.4")
+        B = decout[0].shape[0]
+        n = nh * nw
+        ap = pre + ".act_postprocess"
+        tok = [ops.split(decout[k].float().reshape(B * n, -1), self.x3) for k in hooks]
+        # act_postprocess: 1x1 convs are per-token linears; ConvTranspose(k=s) is a linear to (cout, i, j) + rearrangement
+        def convT(t, name, k):
+            cout = self._sd[name + ".bias"].shape[0]
+            r, _ = ops.linear(t, self._w[name + ".weight"], None, B * n, x3=self.x3)        # [B*n, cout*k*k]
+            r = r.view(B, nh, nw, cout, k, k).permute(0, 1, 4, 2, 5, 3).reshape(B, nh * k, nw * k, cout)
+            return (r + self._sd[name + ".bias"]).contiguous()
+        _, t0 = self._c1(tok[0], B * n, ap + ".0.0", want_fp32=False, want_split=True)
+        _, t1 = self._c1(tok[1], B * n, ap + ".1.0", want_fp32=False, want_split=True)
+        l0 = convT(t0, ap + ".0.1", 4)                                                      # [B, 4nh, 4nw, 96]
+        l1 = convT(t1, ap + ".1.1", 2)                                                      # [B, 2nh, 2nw, 192]
+        _, l2s = self._c1(tok[2], B * n, ap + ".2.0", want_fp32=False, want_split=True)      # [B*n, 384]
+        _, t3 = self._c1(tok[3], B * n, ap + ".3.0", want_fp32=False, want_split=True)       # [B*n, 768]
+        # 3x3 stride-2 pad-1 conv == the stride-1 conv sampled at even pixels
+        t3 = Split(t3.hi.view(B, nh, nw, -1), t3.lo.view(B, nh, nw, -1) if t3.lo is not None else None)
+        l3f, _ = self._c3(t3, B, nh, nw, ap + ".3.1")
+        l3 = l3f[:, ::2, ::2].contiguous()
+        h3, w3 = l3.shape[1], l3.shape[2]
+        rn = pre + ".scratch.layer"
+        kw = dict(want_fp32=True, want_split=True, split_relu=True)
+        f0 = self._c3(ops.split(l0, self.x3), B, 4 * nh, 4 * nw, rn + "1_rn", **kw)
+        f1 = self._c3(ops.split(l1, self.x3), B, 2 * nh, 2 * nw, rn + "2_rn", **kw)
+        f2 = self._c3(Split(l2s.hi.view(B, nh, nw, -1), l2s.lo.view(B, nh, nw, -1) if l2s.lo is not None else None),
+                      B, nh, nw, rn + "3_rn", **kw)
+        f3 = self._c3(ops.split(l3, self.x3), B, h3, w3, rn + "4_rn", **kw)
+        sc = pre + ".scratch.refinenet"
+        p4 = self._fusion(sc + "4", B, h3, w3, f3[0], f3[1])[:, :nh, :nw].contiguous()
+        p3 = self._fusion(sc + "3", B, nh, nw, p4, x1=f2)
+        p2 = self._fusion(sc + "2", B, 2 * nh, 2 * nw, p3, x1=f1)
+        p1 = self._fusion(sc + "1", B, 4 * nh, 4 * nw, p2, x1=f0)                           # [B, 8nh, 8nw, 256]
+        o, _ = self._c3(ops.split(p1, self.x3), B, 8 * nh, 8 * nw, pre + ".head.0")
+        o = self._up2(o)                                                                    # [B, H, W, 128]
+        _, o = self._c3(ops.split(o, self.x3), B, H, W, pre + ".head.2", act=2, want_fp32=False, want_split=True)
+        out, _ = self._c1(Split(o.hi.view(B * H * W, -1), o.lo.view(B * H * W, -1) if o.lo is not None else None),
+                          B * H * W, pre + ".head.4")
+        return out.view(B, H, W, -1)                                                        # NHWC, 4 channels
 
     @torch.no_grad()
     def _downstream_head(self, head_num, decout, img_shape, raw: bool = False):
@@ -265,23 +320,16 @@ class AsymmetricMASt3R:
         pre = f"downstream_head{head_num}"
         dev = decout[0].device
         with torch.cuda.device(dev):
-            prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-            torch.backends.cudnn.allow_tf32 = False
-            torch.backends.cuda.matmul.allow_tf32 = False
-            try:
-                pts = self._dpt(pre + ".dpt", decout, H, W)
-            finally:
-                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+            pts = self._dpt(pre + ".dpt", decout, H, W)                      # NHWC [B, H, W, 4]
             cat = torch.cat([decout[0].float(), decout[-1].float()], -1)
             B, S, D = cat.shape
             a = ops.split(cat.reshape(B * S, D), self.x3)
             _, hdn = self._linear(a, pre + ".head_local_features.fc1", B * S, act=1, want_fp32=False, want_split=True)
             lf, _ = self._linear(hdn, pre + ".head_local_features.fc2", B * S)
             lf = F.pixel_shuffle(lf.view(B, S, -1).transpose(-1, -2).reshape(B, -1, H // 16, W // 16), 16)
-            out = torch.cat([pts, lf], 1)
+            fmap = torch.cat([pts, lf.permute(0, 2, 3, 1)], -1)             # B,H,W,29
             if raw:
-                return out
-            fmap = out.permute(0, 2, 3, 1)
+                return fmap.permute(0, 3, 1, 2)
             xyz = fmap[..., 0:3]
             d = xyz.norm(dim=-1, keepdim=True)
             res = dict(pts3d=xyz / d.clip(min=1e-8) * torch.expm1(d), conf=1 + fmap[..., 3].exp())

@@ -10,9 +10,10 @@ from .._lib import f32, i32, i64, vp
 
 _lib.register("adb_gemm_bf16", [i32, i32, i32, i32, vp, vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64,
                                 vp, vp, i64, i64, f32, i32, i32, i64, i64, i64, vp])
+_lib.register("adb_conv3x3_bf16", [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp])
 _lib.register("adb_layernorm", [i64, i32, vp, vp, vp, f32, vp, vp, vp, vp])
 _lib.register("adb_split_bf16", [i64, vp, vp, vp, vp])
-_lib.register("adb_rope_heads", [i32, i32, i32, i64, i32, vp, vp, f32, i32, i32, vp, vp, vp])
+_lib.register("adb_rope_heads", [i32, i32, i32, i64, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp])
 _lib.register("adb_softmax_rows", [i64, i32, i64, i64, vp, vp, vp, vp])
 _lib.register("adb_im2col_patch16", [i32, i32, i32, vp, vp, vp, vp])
 
@@ -90,16 +91,32 @@ def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-6, want_fp32=False, 
     return y, sp
 
 
-def rope_heads(x: torch.Tensor, B, N, h, ld, col0, pos, mode: int, base: float = 100.0, x3=True, Npad=None) -> Split:
+_rope_tables: dict = {}
+
+
+def rope_table(n_pos: int, device, base: float = 100.0) -> torch.Tensor:
+    """(cos, sin) of p * base^(-2i/32), p < n_pos, i < 16 — computed with the reference's own fp32 expressions
+    (croco/models/pos_embed.py:118-127) so the rotation angles are the same numbers."""
+    key = (n_pos, str(device), base)
+    if key not in _rope_tables:
+        D = 32
+        inv_freq = 1.0 / (base ** (torch.arange(0, D, 2).float().to(device) / D))
+        t = torch.arange(n_pos, device=device, dtype=inv_freq.dtype)
+        freqs = torch.einsum("i,j->ij", t, inv_freq)
+        _rope_tables[key] = torch.stack([freqs.cos(), freqs.sin()], -1).contiguous()
+    return _rope_tables[key]
+
+
+def rope_heads(x: torch.Tensor, B, N, h, ld, col0, pos, mode: int, base: float = 100.0, x3=True, Npad=None, n_pos: int = 64) -> Split:
     dev = x.device
     Npad = N if Npad is None else Npad
     shape = (B, h, 64, Npad) if mode == 2 else (B, h, N, 64)
-    alloc = torch.zeros if (mode == 2 and Npad != N) else torch.empty
-    hi = alloc(shape, dtype=BF16, device=dev)
-    lo = alloc(shape, dtype=BF16, device=dev) if x3 else None
+    hi = torch.empty(shape, dtype=BF16, device=dev)
+    lo = torch.empty(shape, dtype=BF16, device=dev) if x3 else None
+    table = rope_table(n_pos, dev, base) if mode == 0 else None
     _lib.call("adb_rope_heads", B, N, h, ld, col0, _lib.ptr(x, torch.float32),
-              _lib.ptr(pos, torch.int64) if pos is not None else None, float(base), mode, Npad, _lib.ptr(hi), _lib.ptr(lo),
-              _lib.stream())
+              _lib.ptr(pos, torch.int64) if pos is not None else None, _lib.ptr(table) if table is not None else None,
+              n_pos, mode, Npad, _lib.ptr(hi), _lib.ptr(lo), _lib.stream())
     return Split(hi, lo)
 
 
@@ -119,3 +136,30 @@ def im2col_patch16(img: torch.Tensor, x3=True) -> Split:
     lo = torch.empty(B * n, 768, dtype=BF16, device=img.device) if x3 else None
     _lib.call("adb_im2col_patch16", B, H, W, _lib.ptr(img.contiguous(), torch.float32), _lib.ptr(hi), _lib.ptr(lo), _lib.stream())
     return Split(hi, lo)
+
+
+def prep_conv3x3_weight(w: torch.Tensor, x3=True) -> Split:
+    """[Cout, Cin, 3, 3] fp32 -> bf16 split [Cout, 9 * Cin_pad] in (ky, kx, ci) order, Cin zero-padded to 64."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    cpad = (Cin + 63) // 64 * 64
+    wp = torch.zeros(Cout, 3, 3, cpad, dtype=torch.float32, device=w.device)
+    wp[..., :Cin] = w.permute(0, 2, 3, 1)
+    return split(wp.reshape(Cout, 9 * cpad), x3)
+
+
+def conv3x3(x: Split, B: int, H: int, W: int, Cin: int, w: Split, bias, Cout: int, *, residual=None, act: int = 0,
+            want_fp32=True, want_split=False, split_relu=False, x3=True):
+    """NHWC 3x3 conv on the tensor-core kernel.  Returns (fp32 [B,H,W,Cout] or None, Split [B,H,W,Cout] or None)."""
+    dev = x.hi.device
+    out = torch.empty(B, H, W, Cout, dtype=torch.float32, device=dev) if want_fp32 else None
+    sp = None
+    if want_split:
+        sp = Split(torch.empty(B, H, W, Cout, dtype=BF16, device=dev),
+                   torch.empty(B, H, W, Cout, dtype=BF16, device=dev) if x3 else None)
+    use3 = x.lo is not None and w.lo is not None
+    _lib.call("adb_conv3x3_bf16", B, H, W, Cin, Cout, _lib.ptr(x.hi), _lib.ptr(x.lo) if use3 else None, _lib.ptr(w.hi),
+              _lib.ptr(w.lo) if use3 else None, _lib.ptr(bias) if bias is not None else None,
+              _lib.ptr(residual) if residual is not None else None, _lib.ptr(out) if out is not None else None,
+              _lib.ptr(sp.hi) if sp is not None else None,
+              _lib.ptr(sp.lo) if (sp is not None and sp.lo is not None) else None, int(act), int(split_relu), _lib.stream())
+    return out, sp

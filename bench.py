@@ -143,6 +143,114 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+MAST3R_FLOP_PER_PAIR = 2.806e12   # SURVEY.md §8a (torch FlopCounterMode on the reference module, 512x512)
+
+
+def bench_mast3r(dev, world, rank, steps, warmup, want_cpu):
+    """MASt3R pair inference (2x _encode_image + _decoder + 2x _downstream_head) at 512x512, B pairs per GPU per step;
+    pairs are split across GPUs with no collective."""
+    import torch.distributed as dist
+    from artdeco_b200 import _lib
+    from artdeco_b200.mast3r import FULL_CFG, AsymmetricMASt3R, forward_pair
+    from artdeco_b200.mast3r.shapes import random_state_dict
+    B = 2
+    sd = random_state_dict(FULL_CFG, dev, seed=0)
+    model = AsymmetricMASt3R(precision="bf16x3", **FULL_CFG).load_state_dict(sd).to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    h1 = (torch.rand(B, 3, 512, 512, generator=g) * 2 - 1).pin_memory()
+    h2 = (torch.rand(B, 3, 512, 512, generator=g) * 2 - 1).pin_memory()
+    d1, d2 = h1.to(dev), h2.to(dev)
+    out_host = [torch.empty(B, 512, 512, 4).pin_memory() for _ in range(2)]
+
+    def step():
+        forward_pair(model, d1, d2)
+
+    def e2e_step():
+        a, b = h1.to(dev, non_blocking=True), h2.to(dev, non_blocking=True)
+        r1, r2 = forward_pair(model, a, b)
+        for o, r in zip(out_host, (r1, r2)):
+            o[..., :3].copy_(r["pts3d"], non_blocking=True)
+            o[..., 3].copy_(r["conf"], non_blocking=True)
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / k
+
+    k = max(3, min(steps, 10))
+    ms = timed(step, k, max(3, warmup))
+    ms_e2e = timed(e2e_step, k, 3)
+    # live duration of the dominant kernel (the tcgen05 GEMM / conv kernel) over one step
+    for name in ("adb_gemm_bf16", "adb_conv3x3_bf16", "adb_layernorm", "adb_split_bf16", "adb_rope_heads",
+                 "adb_softmax_rows", "adb_im2col_patch16"):
+        _lib.LAUNCHES.setdefault(name, 1)
+    _lib.TIMER = _lib.StageTimer()
+    step()
+    torch.cuda.synchronize()
+    tot = _lib.TIMER.totals_ms()
+    launches = _lib.TIMER.launches
+    _lib.TIMER = None
+    gemm_ms = sum(tot.get(n, (0.0, 0))[0] for n in ("adb_gemm_bf16", "adb_conv3x3_bf16"))
+    pairs_s = world * B / (ms * 1e-3)
+    peaks = {}
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        with open(pth) as f:
+            peaks = json.load(f)
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+    algo_tf = MAST3R_FLOP_PER_PAIR * B / (gemm_ms * 1e-3) / 1e12          # over the GEMM kernel's own time
+    res = {
+        "metric": "MASt3R pairs/s @512^2", "value": pairs_s, "unit": "pairs/s", "ms_per_step": ms, "pairs_per_gpu_per_step": B,
+        "precision": "bf16x3 (3 tcgen05 MMAs per product: fp32-class accuracy, 1e-4 pointmap tolerance)",
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": 2 * h1.numel() * 4, "d2h_bytes_per_step": 2 * out_host[0].numel() * 4,
+                "what": "two image batches from pinned host memory -> forward_pair -> pts3d+conf of both views copied back"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)",
+                     "achieved": algo_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": algo_tf / peak_tf,
+                     "tensor_work_achieved": 3 * algo_tf, "tensor_work_frac": 3 * algo_tf / peak_tf,
+                     "peak_source": peak_src, "traffic": None, "kernel_ms_per_step": gemm_ms,
+                     "note": "achieved = 2.806 TFLOP/pair algorithmic FLOPs / live GEMM-kernel time; bf16x3 issues 3x that "
+                             "many tensor FLOPs (tensor_work_*), which is what the pipe actually sustains",
+                     "whole_step": {"achieved": MAST3R_FLOP_PER_PAIR * B / (ms * 1e-3) / 1e12,
+                                    "frac": MAST3R_FLOP_PER_PAIR * B / (ms * 1e-3) / 1e12 / peak_tf},
+                     "stage_ms": {k2.replace("adb_", ""): v[0] for k2, v in tot.items()}},
+    }
+    if want_cpu and rank == 0:
+        from oracle import mast3r_torch as mt
+        sd_cpu = {k2: v.cpu() for k2, v in sd.items()}
+        torch.set_num_threads(os.cpu_count() or 1)
+        i1, i2 = h1[:1].clone(), h2[:1].clone()
+        ts = []
+        with torch.inference_mode():
+            for i in range(2):
+                t0 = time.perf_counter()
+                mt.forward_pair(sd_cpu, FULL_CFG, i1, i2)
+                if i:
+                    ts.append(time.perf_counter() - t0)
+        res["cpu_baseline"] = {"value": 1.0 / ts[0], "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "1 warm-up + 1 timed 512x512 pair through oracle/mast3r_torch.py (PyTorch CPU fp32, all host threads)",
+                               "seconds_per_pair": ts[0]}
+    del model, sd
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -300,6 +408,10 @@ def main():
         except Exception:
             pass
 
+    # free the rasterizer's working set before the MASt3R leg
+    del params, t, flat
+    torch.cuda.empty_cache()
+    mast3r = bench_mast3r(dev, world, rank, args.steps, args.warmup, want_cpu=(world == 1 and not args.no_cpu_baseline))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -325,6 +437,7 @@ def main():
                 "what": "rasterization()+L1+fused_ssim loss+backward via autograd; camera and gt image from pinned host memory, loss read back"},
         "gpu_launches": launches,
         "roofline": roofline,
+        "mast3r": mast3r,
     }
     if cpu:
         line["cpu_baseline"] = cpu

@@ -115,11 +115,18 @@ int adb_gemm_bf16(int batch, int M, int N, int K, const void* A_hi, const void* 
                   void* D_hi, void* D_lo, long long ldo, long long sO, const float* bias, const float* residual,
                   long long ldr, long long sR, float alpha, int act /*0 none, 1 GELU(erf)*/, int zdiv, long long sD2,
                   long long sO2, long long sR2, adb_stream_t stream);
+/* adb_conv3x3_bf16: 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on the same kernel (4-D TMA boxes, no im2col):
+ *   replaces the nn.Conv2d(k=3) calls of croco/models/dpt_block.py:20-77,93-112,368-372.  x NHWC bf16 split, w bf16 split
+ *   [Cout][9*Cin_pad] tap-major with Cin padded to 64; outputs NHWC; act 0/2 (ReLU); split_relu: split stores relu(v). */
+int adb_conv3x3_bf16(int B, int H, int W, int Cin, int Cout, const void* x_hi, const void* x_lo, const void* w_hi,
+                     const void* w_lo, const float* bias, const float* residual, float* D, void* D_hi, void* D_lo, int act,
+                     int split_relu, adb_stream_t stream);
 int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
                   void* y_hi, void* y_lo, adb_stream_t stream);
 int adb_split_bf16(long long n, const float* x, void* hi, void* lo, adb_stream_t stream);
 int adb_rope_heads(int B, int N, int h, long long ld, int col0, const float* x, const long long* pos /*[B,N,2] (y,x)*/,
-                   float base, int mode, int Npad, void* hi, void* lo, adb_stream_t stream);
+                   const float* table /*[n_pos][16][2] (cos,sin)*/, int n_pos, int mode, int Npad, void* hi, void* lo,
+                   adb_stream_t stream);
 int adb_softmax_rows(long long rows, int L, long long ld_in, long long ld_out, const float* s, void* hi, void* lo,
                      adb_stream_t stream);
 int adb_im2col_patch16(int B, int H, int W, const float* img, void* hi, void* lo, adb_stream_t stream);
