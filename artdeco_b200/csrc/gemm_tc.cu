@@ -133,6 +133,20 @@ __device__ __forceinline__ uint32_t make_idesc() {
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32 B sector per lane per instruction
+__device__ __forceinline__ void st_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st_v8_b32(void* p, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void ld_v8_nc(const float* p, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]),
+                 "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+
 struct TileCoord {
     int bz, mt, nt;
 };
@@ -272,9 +286,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             const size_t dbase = (size_t)zo * p.sD2 + (size_t)zi * p.sD;
             const size_t obase = (size_t)zo * p.sO2 + (size_t)zi * p.sO;
             const size_t rbase = (size_t)zo * p.sR2 + (size_t)zi * p.sR;
-            const bool vec_ok = (p.ldd % 4 == 0) && (p.ldr % 4 == 0) && (p.ldo % 8 == 0) && (p.N % 4 == 0) &&
-                                (((uintptr_t)p.D | (uintptr_t)p.residual | (uintptr_t)p.Dhi | (uintptr_t)p.Dlo) % 16 == 0) &&
-                                ((dbase | rbase) % 4 == 0) && (obase % 8 == 0);
+            // 256-bit accesses need 32 B alignment of every row segment
+            const bool vec_ok = (p.ldd % 8 == 0) && (p.ldr % 8 == 0) && (p.ldo % 16 == 0) &&
+                                (((uintptr_t)p.D | (uintptr_t)p.residual | (uintptr_t)p.Dhi | (uintptr_t)p.Dlo) % 32 == 0) &&
+                                ((dbase | rbase) % 8 == 0) && (obase % 16 == 0);
             // The tensor core's fp32 accumulator truncates, so its error grows linearly with the length of the
             // accumulation chain (measured: 1.2e-6 at K=1024, 2e-5 at K=16384).  Partial sums are therefore taken
             // out of TMEM every KCHUNK_KB k-blocks and added here in round-to-nearest fp32 registers.
@@ -329,36 +344,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 }
                 if (vec_ok && c0 + 32 <= p.N) {
                     if (p.residual) {
-                        const float4* rp = reinterpret_cast<const float4*>(p.residual + rbase + (size_t)row * p.ldr + c0);
+                        const float* rp = p.residual + rbase + (size_t)row * p.ldr + c0;
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 rs = __ldg(rp + j4);
-                            v[4 * j4] += rs.x; v[4 * j4 + 1] += rs.y; v[4 * j4 + 2] += rs.z; v[4 * j4 + 3] += rs.w;
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            float rs[8];
+                            ld_v8_nc(rp + 8 * j8, rs);
+#pragma unroll
+                            for (int k2 = 0; k2 < 8; ++k2) v[8 * j8 + k2] += rs[k2];
                         }
                     }
                     if (p.D) {
-                        float4* dp = reinterpret_cast<float4*>(p.D + dbase + (size_t)row * p.ldd + c0);
+                        float* dp = p.D + dbase + (size_t)row * p.ldd + c0;
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) dp[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                        for (int j8 = 0; j8 < 4; ++j8) st_v8(dp + 8 * j8, v + 8 * j8);
                     }
                     if (p.Dhi) {
-                        uint4* hp = reinterpret_cast<uint4*>(p.Dhi + obase + (size_t)row * p.ldo + c0);
-                        uint4* lp = p.Dlo ? reinterpret_cast<uint4*>(p.Dlo + obase + (size_t)row * p.ldo + c0) : nullptr;
+                        uint32_t hw[16], lw[16];
 #pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            uint32_t hw[4], lw[4];
-#pragma unroll
-                            for (int k2 = 0; k2 < 4; ++k2) {
-                                float a = v[8 * j8 + 2 * k2], b = v[8 * j8 + 2 * k2 + 1];
-                                if (p.split_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                                const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-                                const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-                                const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-                                hw[k2] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-                                lw[k2] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-                            }
-                            hp[j8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            if (lp) lp[j8] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        for (int k2 = 0; k2 < 16; ++k2) {
+                            float a = v[2 * k2], b = v[2 * k2 + 1];
+                            if (p.split_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+                            const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+                            const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+                            hw[k2] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+                            lw[k2] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+                        }
+                        __nv_bfloat16* hp = p.Dhi + obase + (size_t)row * p.ldo + c0;
+                        st_v8_b32(hp, hw); st_v8_b32(hp + 16, hw + 8);
+                        if (p.Dlo) {
+                            __nv_bfloat16* lp = p.Dlo + obase + (size_t)row * p.ldo + c0;
+                            st_v8_b32(lp, lw); st_v8_b32(lp + 16, lw + 8);
                         }
                     }
                 } else {

@@ -17,8 +17,8 @@ __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* lo
     if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// one warp per row, C <= 32*MAXPER
-template <int MAXPER>
+// one warp per row; lane owns 8 consecutive channels per 256-channel chunk (two LDG.128 in, one 128-bit bf16 store out)
+template <int CHUNKS>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(long long rows, int C, const float* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* __restrict__ y, __nv_bfloat16* __restrict__ yhi,
@@ -27,33 +27,62 @@ layernorm_kernel(long long rows, int C, const float* __restrict__ x, const float
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* xr = x + (size_t)row * C;
-    float v[MAXPER];
+    float v[CHUNKS][8];
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        const int c = lane + 32 * k;
-        v[k] = c < C ? xr[c] : 0.f;
-        sum += v[k];
+    for (int k = 0; k < CHUNKS; ++k) {
+        const int c = k * 256 + lane * 8;
+        if (c < C) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + c), b = *reinterpret_cast<const float4*>(xr + c + 4);
+            v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w; v[k][4] = b.x; v[k][5] = b.y; v[k][6] = b.z; v[k][7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[k][e];
     }
     sum = adb_warp_sum(sum);
     const float mean = sum / (float)C;
     float var = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        const int c = lane + 32 * k;
-        const float d = c < C ? v[k] - mean : 0.f;
-        var += d * d;
+    for (int k = 0; k < CHUNKS; ++k) {
+        if (k * 256 + lane * 8 < C) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = v[k][e] - mean; var += d * d; }
+        }
     }
     var = adb_warp_sum(var) / (float)C;
     const float rstd = 1.0f / sqrtf(var + eps);
 #pragma unroll
-    for (int k = 0; k < MAXPER; ++k) {
-        const int c = lane + 32 * k;
+    for (int k = 0; k < CHUNKS; ++k) {
+        const int c = k * 256 + lane * 8;
         if (c < C) {
-            const float o = (v[k] - mean) * rstd * gamma[c] + beta[c];
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (v[k][e] - mean) * rstd * gg[e] + bb[e];
             const size_t i = (size_t)row * C + c;
-            if (y) y[i] = o;
-            if (yhi) split_store(yhi, ylo, i, o);
+            if (y) {
+                *reinterpret_cast<float4*>(y + i) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(y + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            if (yhi) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat16 ah = __float2bfloat16_rn(o[2 * e]), bh = __float2bfloat16_rn(o[2 * e + 1]);
+                    const __nv_bfloat16 al = __float2bfloat16_rn(o[2 * e] - __bfloat162float(ah));
+                    const __nv_bfloat16 bl = __float2bfloat16_rn(o[2 * e + 1] - __bfloat162float(bh));
+                    hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+                    lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+                }
+                *reinterpret_cast<uint4*>(yhi + i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                if (ylo) *reinterpret_cast<uint4*>(ylo + i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
         }
     }
 }
@@ -154,7 +183,60 @@ heads_transpose_kernel(int N, int h, long long ld, int col0, const float* __rest
     }
 }
 
-// one warp per row of length L (row stride ld_in for the fp32 input, ld_out for the bf16 outputs)
+// one warp per row of length L (row stride ld_in for the fp32 input, ld_out for the bf16 outputs).  The row is read
+// ONCE into registers (4 values per lane per 128-column chunk, LDG.128) when L <= 128*CH and L % 4 == 0.
+template <int CH>
+__global__ void __launch_bounds__(256)
+softmax_reg_kernel(long long rows, int L, long long ld_in, long long ld_out, const float* __restrict__ s,
+                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* sr = s + (size_t)row * ld_in;
+    float v[CH][4];
+    float m = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int c = k * 128 + lane * 4;
+        if (c < L) {
+            const float4 a = *reinterpret_cast<const float4*>(sr + c);
+            v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w;
+            m = fmaxf(m, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+        if (k * 128 + lane * 4 < L) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { v[k][e] = expf(v[k][e] - m); sum += v[k][e]; }
+        }
+    sum = adb_warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int c = k * 128 + lane * 4;
+        if (c < L) {
+            uint32_t hw[2], lw[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float a = v[k][2 * e] * inv, b = v[k][2 * e + 1] * inv;
+                const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+                const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+                const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+                hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+                lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+            }
+            const size_t o = (size_t)row * ld_out + c;
+            *reinterpret_cast<uint2*>(hi + o) = make_uint2(hw[0], hw[1]);
+            if (lo) *reinterpret_cast<uint2*>(lo + o) = make_uint2(lw[0], lw[1]);
+        }
+    }
+}
+
+// generic fallback (any L / alignment): three passes over the row
 __global__ void __launch_bounds__(256)
 softmax_kernel(long long rows, int L, long long ld_in, long long ld_out, const float* __restrict__ s,
                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -195,14 +277,14 @@ inline int grid_for(long long n) { long long g = (n + 255) / 256; return (int)(g
 
 ADB_API int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps,
                           float* y, void* y_hi, void* y_lo, cudaStream_t stream) {
-    ADB_REQUIRE(rows >= 0 && C >= 1 && C <= 2048, "adb_layernorm: C must be in [1, 2048]");
+    ADB_REQUIRE(rows >= 0 && C >= 8 && C <= 2048 && C % 8 == 0, "adb_layernorm: C must be a multiple of 8 in [8, 2048]");
     if (rows == 0) return ADB_OK;
     ADB_REQUIRE(x && gamma && beta && (y || y_hi), "adb_layernorm: null pointer");
     const int blocks = (int)((rows + 7) / 8);
     if (C <= 1024)
-        layernorm_kernel<32><<<blocks, 256, 0, stream>>>(rows, C, x, gamma, beta, eps, y, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+        layernorm_kernel<4><<<blocks, 256, 0, stream>>>(rows, C, x, gamma, beta, eps, y, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
     else
-        layernorm_kernel<64><<<blocks, 256, 0, stream>>>(rows, C, x, gamma, beta, eps, y, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+        layernorm_kernel<8><<<blocks, 256, 0, stream>>>(rows, C, x, gamma, beta, eps, y, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
     ADB_CHECK_LAUNCH("layernorm_kernel");
     return ADB_OK;
 }
@@ -241,7 +323,15 @@ ADB_API int adb_softmax_rows(long long rows, int L, long long ld_in, long long l
     ADB_REQUIRE(rows >= 0 && L >= 1, "adb_softmax_rows: bad sizes");
     if (rows == 0) return ADB_OK;
     ADB_REQUIRE(s && hi, "adb_softmax_rows: null pointer");
-    softmax_kernel<<<(int)((rows + 7) / 8), 256, 0, stream>>>(rows, L, ld_in, ld_out, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    const bool fast = (L % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && ((uintptr_t)s % 16 == 0) &&
+                      ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0) && L <= 2048;
+    const int blocks = (int)((rows + 7) / 8);
+    if (fast && L <= 1024)
+        softmax_reg_kernel<8><<<blocks, 256, 0, stream>>>(rows, L, ld_in, ld_out, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    else if (fast)
+        softmax_reg_kernel<16><<<blocks, 256, 0, stream>>>(rows, L, ld_in, ld_out, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    else
+        softmax_kernel<<<blocks, 256, 0, stream>>>(rows, L, ld_in, ld_out, s, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
     ADB_CHECK_LAUNCH("softmax_kernel");
     return ADB_OK;
 }

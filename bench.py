@@ -26,6 +26,13 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_T0 = time.time()
+
+
+def log(msg):
+    """Progress to stderr (stdout carries exactly one JSON line)."""
+    print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -191,6 +198,7 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_cpu):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / k
 
+    log("mast3r model resident; timing")
     k = max(3, min(steps, 10))
     ms = timed(step, k, max(3, warmup))
     ms_e2e = timed(e2e_step, k, 3)
@@ -232,9 +240,9 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_cpu):
                      "stage_ms": {k2.replace("adb_", ""): v[0] for k2, v in tot.items()}},
     }
     if want_cpu and rank == 0:
+        log("mast3r GPU legs done; timing the CPU oracle (PyTorch fp32) on one pair")
         from oracle import mast3r_torch as mt
         sd_cpu = {k2: v.cpu() for k2, v in sd.items()}
-        torch.set_num_threads(os.cpu_count() or 1)
         i1, i2 = h1[:1].clone(), h2[:1].clone()
         ts = []
         with torch.inference_mode():
@@ -288,13 +296,9 @@ def main():
     campos = torch.inverse(Vd)[:3, 3].contiguous()
     Ng = N_GAUSS
     # flat gradient buffer [N,59]: one NCCL bucket, per-parameter views written directly by the backward kernel
-    flat = torch.empty(Ng * 59, dtype=torch.float32, device=dev)
-    o = 0
-    gviews = {}
-    for name, m in (("means", 3), ("quats", 4), ("scales", 3), ("opacities", 1), ("sh", 48)):
-        gviews[name] = flat[o:o + Ng * m].view((Ng, m) if m > 1 else (Ng,))
-        o += Ng * m
-    gviews["sh"] = gviews["sh"].view(Ng, 16, 3)
+    from artdeco_b200.parallel import GradBucket
+    bucket = GradBucket(Ng, dev)
+    flat, gviews = bucket.flat, bucket.views
     v_view = torch.zeros(4, 4, device=dev)
     v_campos = torch.zeros(3, device=dev)
     stats = {}
@@ -312,8 +316,7 @@ def main():
                   _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(v_splats), _lib.ptr(gviews["means"]),
                   _lib.ptr(gviews["quats"]), _lib.ptr(gviews["scales"]), _lib.ptr(gviews["opacities"]),
                   _lib.ptr(gviews["sh"]), _lib.ptr(v_view), _lib.ptr(v_campos), _lib.stream())
-        if world > 1:
-            dist.all_reduce(flat)
+        bucket.all_reduce()
         stats["n_isect"] = n_isect
         stats["n_visible"] = None
 
@@ -338,9 +341,9 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    log("raster scene resident; timing device-resident steps")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step = timed(step, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
 
     # per-stage live timing + launch count over K more steps (events on the launching stream)
     _lib.TIMER = _lib.StageTimer()
@@ -352,6 +355,7 @@ def main():
     _lib.TIMER = None
     stage_ms = {k.replace("adb_raster_", ""): v[0] / v[1] for k, v in tot.items()}
 
+    log(f"raster value leg done: {ms_step:.3f} ms/step")
     # ---- e2e through the public operator surface, host buffers for the per-step inputs ----
     gt_host = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(2)).pin_memory()
     V_host, K_host = V.clone().pin_memory(), K.clone().pin_memory()
@@ -408,14 +412,17 @@ def main():
         except Exception:
             pass
 
+    log(f"raster e2e leg done: {ms_e2e:.3f} ms/step")
     # free the rasterizer's working set before the MASt3R leg
-    del params, t, flat
+    del params, t, flat, bucket, gviews
     torch.cuda.empty_cache()
     mast3r = bench_mast3r(dev, world, rank, args.steps, args.warmup, want_cpu=(world == 1 and not args.no_cpu_baseline))
+    clocks = sampler.stop() if sampler else None   # sampled across every timed GPU leg (raster, e2e, MASt3R)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    log(f"mast3r leg done: {mast3r['ms_per_step']:.2f} ms/step")
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         g, sec, _, threads = cpu_oracle_leg(3, 1, N_GAUSS, 3.5)
