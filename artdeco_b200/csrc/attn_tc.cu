@@ -1,0 +1,419 @@
+// Fused attention on tcgen05: O = softmax(scale * Q K^T) V for one (batch*head, 128-query tile) per CTA, with the
+// score matrix resident in TENSOR MEMORY — S and P never touch HBM.
+//
+// Replaces the reference's materialised attention
+//   attn = (q @ k.transpose(-2,-1)) * scale; attn = attn.softmax(-1); x = attn @ v
+// (VSLAM/thirdparty/mast3r/dust3r/croco/models/blocks.py:105-109 self-attention, :162-166 cross-attention), which
+// the reference runs as three torch kernels with a [B,h,N,N] fp32 tensor written and read twice.
+//
+// Structure (head_dim = 64, keys processed in blocks of 128):
+//   TMA producer warp     Q tile once; K blocks through a 2-stage ring (read twice: see below); V^T blocks (1 stage)
+//   MMA warp (1 thread)   S_j = Q K_j^T  (tcgen05.mma M128 N128 K16, bf16x3 = 12 MMAs) into one of two TMEM S buffers;
+//                         O += P_j V_j   (M128 N64 K16, bf16x3 = 24 MMAs) into a TMEM O accumulator
+//   4 softmax warps       thread == query row.  PASS 1 reads every S_j and keeps only the row maximum.  PASS 2 recomputes
+//                         S_j (the tensor pipe is cheap here), forms p = exp2((s - max) * scale*log2e), accumulates the row
+//                         sum, and writes P_j as a bf16 (hi, lo) pair straight into shared memory in the 128-byte-swizzled
+//                         K-major layout the UMMA descriptor expects — the A operand of the P V product.
+//   Two passes instead of an online-softmax rescale: the running-max correction would need a TMEM read-modify-write of O
+//   per key block; recomputing Q K^T costs 12 extra MMAs per block and keeps O a pure accumulate chain.
+// Precision: bf16x3 everywhere (same contract as csrc/gemm_tc.cu); exp via ex2.approx (2 ulp).
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int NT = 192;                  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 softmax
+constexpr int QT = 128, KT = 128, HD = 64;
+constexpr int TILE16 = 128 * 64 * 2;     // [128 rows x 64 cols] bf16 = 16 KB
+constexpr int TILE8 = 64 * 64 * 2;       // [64 rows x 64 cols] bf16 = 8 KB
+constexpr int TMEM_COLS = 512;
+constexpr int O_COL = 256;
+
+struct AttnParams {
+    int Nq, Nk, heads, n_qtiles;
+    float scale_log2e;
+    __nv_bfloat16* Ohi; __nv_bfloat16* Olo;   // [B, Nq, heads*64]
+    int nterms;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    uint32_t d = 0;
+    d |= 1u << 4; d |= 1u << 7; d |= 1u << 10;
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(128 >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared memory map (bytes, 1024-aligned tiles)
+constexpr int OFF_Q = 0;                       // Q hi, Q lo            2 x 16 KB
+constexpr int OFF_K = OFF_Q + 2 * TILE16;      // 2 stages x (K hi, K lo)   64 KB
+constexpr int OFF_V = OFF_K + 4 * TILE16;      // V^T: 2 key-chunks x (hi, lo) x 8 KB = 32 KB
+constexpr int OFF_P = OFF_V + 4 * TILE8;       // P: 2 key-chunks x (hi, lo) x 16 KB = 64 KB
+constexpr int OFF_BAR = OFF_P + 4 * TILE16;    // barriers
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 6, B_SFULL = 7, B_SEMPTY = 9, B_PFULL = 11,
+       B_PEMPTY = 12, B_OFULL = 13, B_COUNT = 14 };
+
+__global__ void __launch_bounds__(NT, 1)
+attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo,
+                  const __grid_constant__ CUtensorMap mKhi, const __grid_constant__ CUtensorMap mKlo,
+                  const __grid_constant__ CUtensorMap mVhi, const __grid_constant__ CUtensorMap mVlo,
+                  const AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar = (uint64_t*)(smem + OFF_BAR);
+    uint32_t* tmem_ptr = (uint32_t*)(bar + B_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool x3 = p.nterms == 3;
+    const int qt = blockIdx.x % p.n_qtiles, bh = blockIdx.x / p.n_qtiles;
+    const int q0 = qt * QT;
+    const int nb = (p.Nk + KT - 1) / KT;
+    const uint32_t kstage_bytes = (x3 ? 2 : 1) * TILE16, v_bytes = (x3 ? 4 : 2) * TILE8;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(bar + B_QFULL, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar + B_KFULL + s, 1); mbar_init(bar + B_KEMPTY + s, 1);
+            mbar_init(bar + B_SFULL + s, 1); mbar_init(bar + B_SEMPTY + s, 4);
+        }
+        mbar_init(bar + B_VFULL, 1); mbar_init(bar + B_VEMPTY, 1);
+        mbar_init(bar + B_PFULL, 4); mbar_init(bar + B_PEMPTY, 1);
+        mbar_init(bar + B_OFULL, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            mbar_expect_tx(bar + B_QFULL, (x3 ? 2 : 1) * TILE16);
+            tma_load_3d(smem + OFF_Q, &mQhi, bar + B_QFULL, 0, q0, bh);
+            if (x3) tma_load_3d(smem + OFF_Q + TILE16, &mQlo, bar + B_QFULL, 0, q0, bh);
+            for (int it = 0; it < 2 * nb; ++it) {          // K blocks: pass 1 then pass 2
+                const int j = it % nb, s = it & 1;
+                mbar_wait(bar + B_KEMPTY + s, ((it >> 1) & 1) ^ 1);
+                uint8_t* st = smem + OFF_K + s * 2 * TILE16;
+                mbar_expect_tx(bar + B_KFULL + s, kstage_bytes);
+                tma_load_3d(st, &mKhi, bar + B_KFULL + s, 0, j * KT, bh);
+                if (x3) tma_load_3d(st + TILE16, &mKlo, bar + B_KFULL + s, 0, j * KT, bh);
+                if (it >= nb) {                            // pass 2: the matching V^T block (two 64-key chunks)
+                    mbar_wait(bar + B_VEMPTY, (j & 1) ^ 1);
+                    mbar_expect_tx(bar + B_VFULL, v_bytes);
+                    uint8_t* vt = smem + OFF_V;
+                    tma_load_3d(vt, &mVhi, bar + B_VFULL, j * KT, 0, bh);
+                    tma_load_3d(vt + TILE8, &mVhi, bar + B_VFULL, j * KT + 64, 0, bh);
+                    if (x3) {
+                        tma_load_3d(vt + 2 * TILE8, &mVlo, bar + B_VFULL, j * KT, 0, bh);
+                        tma_load_3d(vt + 3 * TILE8, &mVlo, bar + B_VFULL, j * KT + 64, 0, bh);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idS = make_idesc(128), idO = make_idesc(64);
+        const uint32_t qa = smem_u32(smem + OFF_Q);
+        mbar_wait(bar + B_QFULL, 0);
+        tc_fence_after();
+        auto issue_S = [&](int it) {        // S[it&1] = Q K^T for K ring slot it&1
+            const int s = it & 1;
+            mbar_wait(bar + B_KFULL + s, (it >> 1) & 1);
+            mbar_wait(bar + B_SEMPTY + s, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ka = smem_u32(smem + OFF_K + s * 2 * TILE16);
+                const uint64_t dQh = make_smem_desc(qa), dQl = make_smem_desc(qa + TILE16);
+                const uint64_t dKh = make_smem_desc(ka), dKl = make_smem_desc(ka + TILE16);
+                const uint32_t td = tmem_base + s * 128;
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                    tc_mma(td, dQh + adv, dKh + adv, idS, k ? 1u : 0u);
+                    if (x3) {
+                        tc_mma(td, dQh + adv, dKl + adv, idS, 1u);
+                        tc_mma(td, dQl + adv, dKh + adv, idS, 1u);
+                    }
+                }
+                tc_commit(bar + B_KEMPTY + s);
+                tc_commit(bar + B_SFULL + s);
+            }
+            __syncwarp();
+        };
+        for (int it = 0; it < nb; ++it) issue_S(it);                // pass 1
+        issue_S(nb);                                                 // first S of pass 2
+        for (int j = 0; j < nb; ++j) {
+            if (j + 1 < nb) issue_S(nb + j + 1);                     // overlap the next S with this block's softmax
+            mbar_wait(bar + B_PFULL, j & 1);
+            mbar_wait(bar + B_VFULL, j & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t pa = smem_u32(smem + OFF_P), va = smem_u32(smem + OFF_V);
+                const uint32_t td = tmem_base + O_COL;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {                        // two 64-key chunks
+                    const uint64_t dPh = make_smem_desc(pa + c * TILE16), dPl = make_smem_desc(pa + (2 + c) * TILE16);
+                    const uint64_t dVh = make_smem_desc(va + c * TILE8), dVl = make_smem_desc(va + (2 + c) * TILE8);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        tc_mma(td, dPh + adv, dVh + adv, idO, (j | c | k) ? 1u : 0u);
+                        if (x3) {
+                            tc_mma(td, dPh + adv, dVl + adv, idO, 1u);
+                            tc_mma(td, dPl + adv, dVh + adv, idO, 1u);
+                        }
+                    }
+                }
+                tc_commit(bar + B_PEMPTY);
+                tc_commit(bar + B_VEMPTY);
+                if (j == nb - 1) tc_commit(bar + B_OFULL);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== softmax / epilogue warps: thread == query row =====
+        const int q = warp & 3;                    // TMEM lane quarter (warps 2,3,4,5 -> 2,3,0,1)
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float m = -3.0e38f;
+        // PASS 1: row maximum of the raw scores
+        for (int it = 0; it < nb; ++it) {
+            const int s = it & 1;
+            mbar_wait(bar + B_SFULL + s, (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_addr + s * 128 + c * 32, r);
+                const int kbase = it * KT + c * 32;
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (kbase + e < p.Nk) m = fmaxf(m, __uint_as_float(r[e]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar + B_SEMPTY + s);
+        }
+        // PASS 2: p = exp2((s - m) * scale*log2e) -> bf16 (hi, lo) written to swizzled smem; row sum
+        float l = 0.f;
+        const float c1 = p.scale_log2e, c0 = -m * p.scale_log2e;
+        for (int j = 0; j < nb; ++j) {
+            const int it = nb + j, s = it & 1;
+            mbar_wait(bar + B_SFULL + s, (it >> 1) & 1);
+            mbar_wait(bar + B_PEMPTY, (j & 1) ^ 1);            // previous P V product has consumed the P tiles
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_addr + s * 128 + c * 32, r);
+                const int kbase = j * KT + c * 32;
+                // key chunk tile (64 keys) and the 16-byte chunks this 32-key group covers inside the 128 B row
+                uint8_t* th = smem + OFF_P + (c >> 1) * TILE16 + row * 128;
+                uint8_t* tl = th + 2 * TILE16;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {                  // 8 keys = one 16 B chunk
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int k0 = g * 8 + 2 * e;
+                        float a = exp2f(fmaf(__uint_as_float(r[k0]), c1, c0));
+                        float b = exp2f(fmaf(__uint_as_float(r[k0 + 1]), c1, c0));
+                        if (kbase + k0 >= p.Nk) a = 0.f;
+                        if (kbase + k0 + 1 >= p.Nk) b = 0.f;
+                        l += a + b;
+                        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
+                        const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+                        const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
+                        hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
+                        lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+                    }
+                    const int chunk = ((c & 1) * 4 + g) ^ (row & 7);       // SWIZZLE_128B: 16 B chunk index XOR (row % 8)
+                    *reinterpret_cast<uint4*>(th + chunk * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    if (x3) *reinterpret_cast<uint4*>(tl + chunk * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
+            tc_fence_before();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor-core (async) proxy
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar + B_SEMPTY + s); mbar_arrive(bar + B_PFULL); }
+        }
+        // epilogue: O / l -> bf16 split in [B, Nq, heads*64]
+        mbar_wait(bar + B_OFULL, 0);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        const int qrow = q0 + row;
+        const int b = bh / p.heads, hh = bh % p.heads;
+        const size_t o = ((size_t)b * p.Nq + qrow) * (size_t)(p.heads * HD) + (size_t)hh * HD;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_addr + O_COL + c * 32, r);
+            if (qrow < p.Nq) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a = __uint_as_float(r[g * 8 + 2 * e]) * inv, bb = __uint_as_float(r[g * 8 + 2 * e + 1]) * inv;
+                        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(bb);
+                        const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+                        const __nv_bfloat16 bl = __float2bfloat16_rn(bb - __bfloat162float(bh2));
+                        hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
+                        lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+                    }
+                    *reinterpret_cast<uint4*>(p.Ohi + o + c * 32 + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    if (p.Olo) *reinterpret_cast<uint4*>(p.Olo + o + c * 32 + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// bf16 [batch][rows][cols] (cols contiguous); box = 64 cols x box_rows x 1, SWIZZLE_128B
+int make_map(CUtensorMap* map, const void* ptr, long long batch, int rows, int cols, long long ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { adb_set_error_msg("cuTensorMapEncodeTiled driver entry point unavailable"); return ADB_ERR_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows * ld * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { adb_set_error_msg("adb_attention_bf16: cuTensorMapEncodeTiled failed"); return ADB_ERR_INVALID; }
+    return ADB_OK;
+}
+
+}  // namespace
+
+// O[b, n, h*64 + d] = sum_k softmax_k(scale * <Q[b,h,n,:], K[b,h,k,:]>) * V[b,h,k,d]   (head_dim 64)
+//   Q: bf16 split [B*heads, Nq, 64];  K: [B*heads, Nk, 64];  Vt: [B*heads, 64, Nkpad] (Nkpad % 8 == 0, zero padded);
+//   O: bf16 split [B, Nq, heads*64].  *_lo all non-NULL selects bf16x3.
+ADB_API int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, const void* Q_hi, const void* Q_lo,
+                               const void* K_hi, const void* K_lo, const void* Vt_hi, const void* Vt_lo, float scale,
+                               void* O_hi, void* O_lo, cudaStream_t stream) {
+    ADB_REQUIRE(B >= 1 && heads >= 1 && Nq >= 1 && Nk >= 1 && Nkpad >= Nk && Nkpad % 8 == 0, "adb_attention_bf16: bad sizes");
+    ADB_REQUIRE(Q_hi && K_hi && Vt_hi && O_hi, "adb_attention_bf16: null pointer");
+    const bool x3 = Q_lo && K_lo && Vt_lo;
+    ADB_REQUIRE(x3 || (!Q_lo && !K_lo && !Vt_lo), "adb_attention_bf16: give all lo operands or none");
+    ADB_REQUIRE((((uintptr_t)O_hi | (uintptr_t)O_lo) % 16) == 0, "adb_attention_bf16: outputs must be 16-byte aligned");
+    CUtensorMap mQh, mQl, mKh, mKl, mVh, mVl;
+    const long long bh = (long long)B * heads;
+    int rc;
+    if ((rc = make_map(&mQh, Q_hi, bh, Nq, 64, 64, 128))) return rc;
+    if ((rc = make_map(&mKh, K_hi, bh, Nk, 64, 64, 128))) return rc;
+    if ((rc = make_map(&mVh, Vt_hi, bh, 64, Nkpad, Nkpad, 64))) return rc;
+    mQl = mQh; mKl = mKh; mVl = mVh;
+    if (x3) {
+        if ((rc = make_map(&mQl, Q_lo, bh, Nq, 64, 64, 128))) return rc;
+        if ((rc = make_map(&mKl, K_lo, bh, Nk, 64, 64, 128))) return rc;
+        if ((rc = make_map(&mVl, Vt_lo, bh, 64, Nkpad, Nkpad, 64))) return rc;
+    }
+    AttnParams p;
+    p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.n_qtiles = adb_cdiv(Nq, QT);
+    p.scale_log2e = scale * 1.4426950408889634f;
+    p.Ohi = (__nv_bfloat16*)O_hi; p.Olo = (__nv_bfloat16*)O_lo; p.nterms = x3 ? 3 : 1;
+    static bool attr = false;
+    if (!attr) {
+        ADB_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
+    const long long grid = bh * p.n_qtiles;
+    attn_fused_kernel<<<(unsigned)grid, NT, SMEM_BYTES, stream>>>(mQh, mQl, mKh, mKl, mVh, mVl, p);
+    ADB_CHECK_LAUNCH("attn_fused_kernel");
+    return ADB_OK;
+}

@@ -44,6 +44,8 @@ class AsymmetricMASt3R:
             raise ValueError("precision must be 'bf16x3' or 'bf16'")
         self.precision = precision
         self.x3 = precision == "bf16x3"
+        import os
+        self._fused_attn = os.environ.get("ADB_ATTN", "fused") != "materialized"
         self.patch_embed = _PatchEmbedInfo(16)
         self.device = torch.device("cpu")
         self._sd = None          # fp32 tensors (LN params, biases, conv weights)
@@ -127,16 +129,17 @@ class AsymmetricMASt3R:
         return ops.layernorm(x, self._sd[name + ".weight"], self._sd[name + ".bias"], 1e-6, x3=self.x3, **kw)
 
     def _attn_core(self, q: Split, k: Split, vt: Split, B, h, Nq, Nk, Nkpad) -> Split:
+        """softmax(q k^T / 8) v, fused (csrc/attn_tc.cu); ADB_ATTN=materialized selects the three-kernel path kept for A/B."""
+        if self._fused_attn:
+            return ops.attention(q, k, vt, B, h, Nq, Nk, Nkpad, 64 ** -0.5, x3=self.x3)
         dev = q.hi.device
         s = torch.empty(B * h, Nq, Nk, dtype=torch.float32, device=dev)
         ops.gemm(q, k, Nq, Nk, 64, batch=B * h, sA=Nq * 64, sB=Nk * 64, out=s, sD=Nq * Nk, alpha=64 ** -0.5)
-        if Nkpad == Nk:
-            p = ops.softmax_rows(s, B * h * Nq, Nk, Nk, x3=self.x3)
-        else:
-            hi = torch.zeros(B * h * Nq, Nkpad, dtype=torch.bfloat16, device=dev)
-            lo = torch.zeros_like(hi) if self.x3 else None
-            _lib.call("adb_softmax_rows", B * h * Nq, Nk, Nk, Nkpad, _lib.ptr(s), _lib.ptr(hi), _lib.ptr(lo), _lib.stream())
-            p = Split(hi, lo)
+        hi = torch.zeros(B * h * Nq, Nkpad, dtype=torch.bfloat16, device=dev) if Nkpad != Nk else \
+            torch.empty(B * h * Nq, Nkpad, dtype=torch.bfloat16, device=dev)
+        lo = (torch.zeros_like(hi) if Nkpad != Nk else torch.empty_like(hi)) if self.x3 else None
+        _lib.call("adb_softmax_rows", B * h * Nq, Nk, Nk, Nkpad, _lib.ptr(s), _lib.ptr(hi), _lib.ptr(lo), _lib.stream())
+        p = Split(hi, lo)
         C = h * 64
         o = Split(torch.empty(B * Nq, C, dtype=torch.bfloat16, device=dev),
                   torch.empty(B * Nq, C, dtype=torch.bfloat16, device=dev) if self.x3 else None)

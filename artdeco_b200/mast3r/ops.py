@@ -11,6 +11,7 @@ from .._lib import f32, i32, i64, vp
 _lib.register("adb_gemm_bf16", [i32, i32, i32, i32, vp, vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64,
                                 vp, vp, i64, i64, f32, i32, i32, i64, i64, i64, vp])
 _lib.register("adb_conv3x3_bf16", [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp])
+_lib.register("adb_attention_bf16", [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp])
 _lib.register("adb_layernorm", [i64, i32, vp, vp, vp, f32, vp, vp, vp, vp])
 _lib.register("adb_split_bf16", [i64, vp, vp, vp, vp])
 _lib.register("adb_rope_heads", [i32, i32, i32, i64, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp])
@@ -163,3 +164,16 @@ def conv3x3(x: Split, B: int, H: int, W: int, Cin: int, w: Split, bias, Cout: in
               _lib.ptr(sp.hi) if sp is not None else None,
               _lib.ptr(sp.lo) if (sp is not None and sp.lo is not None) else None, int(act), int(split_relu), _lib.stream())
     return out, sp
+
+
+def attention(q: Split, k: Split, vt: Split, B: int, h: int, Nq: int, Nk: int, Nkpad: int, scale: float, x3=True) -> Split:
+    """Fused softmax(scale * q k^T) v on tcgen05 (S/P stay in tensor/shared memory).  q,k: [B,h,N,64]; vt: [B,h,64,Nkpad];
+    returns the bf16 split of the head-merged output [B*Nq, h*64]."""
+    dev = q.hi.device
+    C = h * 64
+    o = Split(torch.empty(B * Nq, C, dtype=BF16, device=dev), torch.empty(B * Nq, C, dtype=BF16, device=dev) if x3 else None)
+    use3 = x3 and q.lo is not None and k.lo is not None and vt.lo is not None
+    _lib.call("adb_attention_bf16", B, h, Nq, Nk, Nkpad, _lib.ptr(q.hi), _lib.ptr(q.lo) if use3 else None, _lib.ptr(k.hi),
+              _lib.ptr(k.lo) if use3 else None, _lib.ptr(vt.hi), _lib.ptr(vt.lo) if use3 else None, float(scale),
+              _lib.ptr(o.hi), _lib.ptr(o.lo) if (use3 and o.lo is not None) else None, _lib.stream())
+    return o

@@ -121,6 +121,12 @@ int adb_gemm_bf16(int batch, int M, int N, int K, const void* A_hi, const void* 
 int adb_conv3x3_bf16(int B, int H, int W, int Cin, int Cout, const void* x_hi, const void* x_lo, const void* w_hi,
                      const void* w_lo, const float* bias, const float* residual, float* D, void* D_hi, void* D_lo, int act,
                      int split_relu, adb_stream_t stream);
+/* adb_attention_bf16: fused softmax(scale * Q K^T) V with the score matrix resident in tensor memory; replaces the three
+ *   materialised torch ops at croco/models/blocks.py:105-109 (self) and :162-166 (cross).  head_dim 64.
+ *   Q [B*heads,Nq,64], K [B*heads,Nk,64], Vt [B*heads,64,Nkpad] bf16 splits; O bf16 split [B,Nq,heads*64]. */
+int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, const void* Q_hi, const void* Q_lo, const void* K_hi,
+                       const void* K_lo, const void* Vt_hi, const void* Vt_lo, float scale, void* O_hi, void* O_lo,
+                       adb_stream_t stream);
 int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
                   void* y_hi, void* y_lo, adb_stream_t stream);
 int adb_split_bf16(long long n, const float* x, void* hi, void* lo, adb_stream_t stream);

@@ -90,3 +90,17 @@ def test_layernorm_softmax_rope_im2col(cuda):
     a = ops.im2col_patch16(img)
     refa = torch.nn.functional.unfold(img, 16, stride=16).transpose(1, 2).reshape(-1, 768)
     assert rel_err(a.hi.float() + a.lo.float(), refa) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,h,Nq,Nk", [(1, 2, 128, 128), (2, 3, 200, 200), (1, 16, 1024, 1024), (2, 12, 768, 768), (1, 2, 12, 12), (1, 2, 300, 130)])
+def test_fused_attention_matches_fp64(cuda, B, h, Nq, Nk):
+    """csrc/attn_tc.cu against softmax(q k^T / 8) v in fp64 (blocks.py:105-109,162-166)."""
+    from artdeco_b200.mast3r import ops
+    q, k, v = _mk((B, h, Nq, 64), 1, cuda), _mk((B, h, Nk, 64), 2, cuda), _mk((B, h, Nk, 64), 3, cuda)
+    Nkpad = (Nk + 7) // 8 * 8
+    vt = torch.zeros(B, h, 64, Nkpad, device=cuda)
+    vt[..., :Nk] = v.transpose(-1, -2)
+    o = ops.attention(ops.split(q), ops.split(k), ops.split(vt), B, h, Nq, Nk, Nkpad, 0.125)
+    ref = (torch.softmax(0.125 * q.double() @ k.double().transpose(-1, -2), -1) @ v.double()).permute(0, 2, 1, 3).reshape(B * Nq, h * 64)
+    assert rel_err(o.hi.float() + o.lo.float(), ref) < 3e-5
