@@ -10,7 +10,7 @@
 // REORDERED into a float4 array (x,y,z,original index), so a row of x-adjacent cells is one contiguous,
 // coalesced bucket scan; each query searches Chebyshev shells r = 0,1,2,.. and stops as soon as the K-th best
 // distance is <= (r*h)^2, which makes the result exact.
-// Squared distances are evaluated as fma(dz,dz,fma(dy,dy,dx*dx)) — the contraction nvcc applies to the
+// Squared distances are evaluated as fma(dz,dz,fma(dx,dx,dy*dy)) — the contraction nvcc applies to the
 // reference's `d.x*d.x + d.y*d.y + d.z*d.z` (simple_knn.cu:136,400) — so distCUDA2 is bit-reproducible.
 #include "common.cuh"
 #include <cfloat>
@@ -230,7 +230,7 @@ knn_query_kernel(long long P, long long Q, int K, const Grid* __restrict__ gp, c
                         if (pid == self) continue;
                         if (candidate && !candidate[pid]) continue;
                         const float dx = p.x - me.x, dy = p.y - me.y, dz = p.z - me.z;
-                        const float dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                        const float dist = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
                         if (dist < best.d[KMAX - 1]) best.push(dist, pid);
                     }
                 }

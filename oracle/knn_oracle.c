@@ -7,7 +7,8 @@
  *   :391-421 updateKBest2 / :423-466 boxKnn2 -> exact K nearest other points (ids + squared distances),
  *                            slot order unspecified; unfilled slots keep FLT_MAX / -1 (spatial.cu:36-37).
  * The distance is d.x*d.x + d.y*d.y + d.z*d.z (:136,:400); nvcc's default -fmad=true contracts it to
- * fma(dz,dz, fma(dy,dy, dx*dx)), reproduced here with fmaf so distCUDA2 can be compared bit-for-bit.
+ * fma(dz,dz, fma(dx,dx, dy*dy)) (SASS of the expression compiled for sm_100: FMUL dy,dy; FFMA dx,dx; FFMA dz,dz),
+ * reproduced here with fmaf so distCUDA2 can be compared bit-for-bit (verified on the GPU against oracle/_ref).
  * PARITY UNPINNED by reference tests (none exist for simple-knn); pinned on the GPU box against the
  * reference extension rebuilt into oracle/_ref (tests/test_knn.py).
  */
@@ -17,7 +18,7 @@
 
 static inline float dist2(const float* a, const float* b) {
     float dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 void adbo_knn_mean3(int P, const float* pts, float* out) {

@@ -196,3 +196,25 @@ def test_knn_1m_properties(cuda):
     bf[torch.arange(256, device=cuda), idx] = float("inf")
     ref = bf.topk(3, largest=False).values
     assert torch.allclose(ref, d[idx], rtol=1e-5, atol=1e-12)
+
+
+def _ref_ext(name):
+    from oracle import build_ref
+    try:
+        return build_ref.load(name)
+    except Exception as e:  # noqa: BLE001  (not built in this checkout, or ABI mismatch)
+        pytest.skip(f"reference extension {name} unavailable: {e}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [5000, 200_000])
+def test_distcuda2_bit_identical_to_the_reference_build(cuda, P):
+    """oracle/_ref/simple_knn_ref.so is the reference's OWN simple_knn.cu compiled for sm_100 (oracle/build_ref.py)."""
+    ref = _ref_ext("simple_knn_ref")
+    from artdeco_b200.knn import distCUDA2, distIndex2
+    pts = synthetic.raster_scene(P, seed=2)["means"].to(cuda)
+    assert torch.equal(ref.distCUDA2(pts), distCUDA2(pts)), "distCUDA2 must equal the reference bit for bit"
+    K = 6
+    dr, _ = ref.distIndex2(pts, K)
+    do, _ = distIndex2(pts, K)
+    assert torch.equal(dr.view(P, K).sort(dim=1).values, do.view(P, K)), "same K nearest distances (reference order is unspecified)"

@@ -82,3 +82,24 @@ def test_ssim_rejects_cpu_tensors(cuda):
     from artdeco_b200.ssim import fused_ssim
     with pytest.raises(_lib.ArtdecoB200Error):
         fused_ssim(torch.rand(1, 3, 16, 16), torch.rand(1, 3, 16, 16))
+
+
+@pytest.mark.gpu
+def test_matches_the_reference_cuda_build(cuda):
+    """oracle/_ref/fused_ssim_ref.so is the reference's OWN ssim.cu compiled for sm_100 (--use_fast_math, as its setup.py does)."""
+    from oracle import build_ref
+    try:
+        ref = build_ref.load("fused_ssim_ref")
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"reference extension unavailable: {e}")
+    from artdeco_b200.ssim import fusedssim, fusedssim_backward
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(2, 3, 270, 480, generator=g).to(cuda), torch.rand(2, 3, 270, 480, generator=g).to(cuda)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    mr, r1, r2, r3 = ref.fusedssim(C1, C2, a, b, True)
+    mo, o1, o2, o3 = fusedssim(C1, C2, a, b, True)
+    assert_close(mo, mr, rtol=1e-5, what="ssim map vs reference build")
+    assert_close(o1, r1, rtol=1e-5, what="dm_dmu1")
+    up = torch.rand(2, 3, 270, 480, generator=g).to(cuda)
+    assert_close(fusedssim_backward(C1, C2, a, b, up, o1, o2, o3), ref.fusedssim_backward(C1, C2, a, b, up, r1, r2, r3),
+                 rtol=1e-5, what="dL/dimg1 vs reference build")
