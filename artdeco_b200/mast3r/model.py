@@ -50,6 +50,7 @@ class AsymmetricMASt3R:
         self.device = torch.device("cpu")
         self._sd = None          # fp32 tensors (LN params, biases, conv weights)
         self._w = {}             # name -> Split (bf16 hi/lo GEMM weights)
+        self._streams = {}
         if any(d % 64 for d in (c["enc_embed_dim"] // c["enc_num_heads"], c["dec_embed_dim"] // c["dec_num_heads"])):
             raise ValueError("head_dim must be 64")
 
@@ -120,6 +121,12 @@ class AsymmetricMASt3R:
                     wkv = torch.cat([raw[p + ".projk.weight"], raw[p + ".projv.weight"]], 0).contiguous().to(dev)
                     self._w[p + ".projkv.weight"] = ops.split(wkv, self.x3)
                     self._sd[p + ".projkv.bias"] = torch.cat([raw[p + ".projk.bias"], raw[p + ".projv.bias"]]).to(dev)
+
+    def _side_stream(self, device):
+        key = torch.device(device).index
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=device)
+        return self._streams[key]
 
     # ---- building blocks ------------------------------------------------------------------------
     def _linear(self, a: Split, name: str, rows: int, **kw):
@@ -220,9 +227,16 @@ class AsymmetricMASt3R:
             g1, _ = self._linear(ops.split(f1.reshape(B * N1, E), self.x3), "decoder_embed", B * N1)
             g2, _ = self._linear(ops.split(f2.reshape(B * N2, E), self.x3), "decoder_embed", B * N2)
             c1, c2 = g1.view(B, N1, Dd), g2.view(B, N2, Dd)
+            # The two decoder sides of a layer only depend on the previous layer's pair, so they run concurrently on two
+            # CUDA streams (at batch 1 each side's GEMMs fill less than half of the 148 SMs on their own).
+            s1 = torch.cuda.current_stream()
+            s2 = self._side_stream(f1.device)
             for i in range(self.cfg["dec_depth"]):
+                s2.wait_stream(s1)
+                with torch.cuda.stream(s2):
+                    n2 = self._dec_block(c2, c1, pos2, pos1, f"dec_blocks2.{i}", h)
                 n1 = self._dec_block(c1, c2, pos1, pos2, f"dec_blocks.{i}", h)
-                n2 = self._dec_block(c2, c1, pos2, pos1, f"dec_blocks2.{i}", h)
+                s1.wait_stream(s2)
                 c1, c2 = n1, n2
                 out1.append(c1)
                 out2.append(c2)
@@ -369,4 +383,14 @@ def forward_pair(model: AsymmetricMASt3R, img1, img2):
     f, pos, _ = model._encode_image(torch.cat((img1, img2), 0), None)
     (f1, f2), (p1, p2) = f.chunk(2, 0), pos.chunk(2, 0)
     d1, d2 = model._decoder(f1.contiguous(), p1.contiguous(), f2.contiguous(), p2.contiguous())
-    return model._downstream_head(1, d1, (H, W)), model._downstream_head(2, d2, (H, W))
+    # the two heads are independent: overlap them on two streams
+    s1 = torch.cuda.current_stream()
+    s2 = model._side_stream(img1.device)
+    s2.wait_stream(s1)
+    with torch.cuda.stream(s2):
+        r2 = model._downstream_head(2, d2, (H, W))
+    r1 = model._downstream_head(1, d1, (H, W))
+    s1.wait_stream(s2)
+    for v in r2.values():
+        v.record_stream(s1)
+    return r1, r2

@@ -160,7 +160,7 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_cpu):
     from artdeco_b200 import _lib
     from artdeco_b200.mast3r import FULL_CFG, AsymmetricMASt3R, forward_pair
     from artdeco_b200.mast3r.shapes import random_state_dict
-    B = 2
+    B = 4
     sd = random_state_dict(FULL_CFG, dev, seed=0)
     model = AsymmetricMASt3R(precision="bf16x3", **FULL_CFG).load_state_dict(sd).to(dev)
     g = torch.Generator().manual_seed(100 + rank)

@@ -71,6 +71,18 @@ int adb_raster_project_bwd(int N, const float* means, const float* quats, const 
                            float* v_scales, float* v_opac, float* v_sh, float* v_viewmat /*[16] +=*/,
                            float* v_campos /*[3] +=*/, adb_stream_t stream);
 
+/* ---- covariance-modulation MLP (SceneModel.render, Reconstruct/scene/scene_models/h3dgsv3.py:656-662; mlp_cov :173-177) ----
+ * x = cat(global_feat[cls_id], local_feat); o = W2 relu(W1 x + b1) + b2; scale_out = scaling*sigmoid(o[:3]);
+ * rot_out = normalize(rotation*o[3:]).  D = Fg+Fl in {32,64}.  Backward ACCUMULATES v_global_feat, v_W1, v_b1, v_W2, v_b2. */
+int adb_cov_mlp_forward(long long N, int Fg, int Fl, const float* global_feat, const float* local_feat,
+                        const long long* cls_id, const float* W1, const float* b1, const float* W2, const float* b2,
+                        const float* scaling, const float* rotation, float* scale_out, float* rot_out, adb_stream_t stream);
+int adb_cov_mlp_backward(long long N, int Fg, int Fl, const float* global_feat, const float* local_feat,
+                         const long long* cls_id, const float* W1, const float* b1, const float* W2, const float* b2,
+                         const float* scaling, const float* rotation, const float* v_scale_out, const float* v_rot_out,
+                         float* v_scaling, float* v_rotation, float* v_local_feat, float* v_global_feat, float* v_W1,
+                         float* v_b1, float* v_W2, float* v_b2, adb_stream_t stream);
+
 /* ---- sparse Adam (in place, no bias correction) ----
  * replaces diff_gaussian_rasterization.adamUpdate / adamUpdateBasic (on-the-fly-nvs fork, un-vendored); call sites
  * Reconstruct/scene/optimizers.py:48-57 (Basic), 90-99, 116-128, 144-156.  visible: uint8/bool [N] or NULL;

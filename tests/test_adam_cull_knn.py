@@ -218,3 +218,43 @@ def test_distcuda2_bit_identical_to_the_reference_build(cuda, P):
     dr, _ = ref.distIndex2(pts, K)
     do, _ = distIndex2(pts, K)
     assert torch.equal(dr.view(P, K).sort(dim=1).values, do.view(P, K)), "same K nearest distances (reference order is unspecified)"
+
+
+# ----------------------------------------------------------------------------- covariance MLP (GPU) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("Fg,Fl,N", [(16, 16, 5000), (32, 32, 3000), (16, 16, 1)])
+def test_cov_mlp_matches_reference_torch_block(cuda, Fg, Fl, N):
+    """The reference block itself (h3dgsv3.py:656-662 with mlp_cov of :173-177) evaluated by torch in fp64 is the oracle."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from artdeco_b200.covmlp import cov_mlp_modulate
+    g = torch.Generator().manual_seed(Fg + N)
+    G = 37
+    D = Fg + Fl
+    mlp = nn.Sequential(nn.Linear(D, D), nn.ReLU(True), nn.Linear(D, 7))
+    with torch.no_grad():
+        for p in mlp.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+    scaling, rotation = torch.rand(N, 3, generator=g) * 0.1, torch.randn(N, 4, generator=g)
+    lf, gf = torch.randn(N, Fl, generator=g), torch.randn(G, Fg, generator=g)
+    cls = torch.randint(0, G, (N, 1), generator=g)
+    vs, vr = torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g)
+    # reference in fp64 on the CPU
+    mlp64 = nn.Sequential(nn.Linear(D, D), nn.ReLU(True), nn.Linear(D, 7)).double()
+    mlp64.load_state_dict({k: v.double() for k, v in mlp.state_dict().items()})
+    ins = [t.double().requires_grad_(True) for t in (scaling, rotation, lf, gf)]
+    sr = mlp64(torch.cat([ins[3][cls.squeeze(-1)], ins[2]], 1))
+    s_ref = ins[0] * torch.sigmoid(sr[:, :3])
+    r_ref = F.normalize(ins[1] * sr[:, 3:])
+    ((s_ref * vs.double()).sum() + (r_ref * vr.double()).sum()).backward()
+    # ours
+    mlp_c = mlp.to(cuda)
+    outs = [t.to(cuda).requires_grad_(True) for t in (scaling, rotation, lf, gf)]
+    s_o, r_o = cov_mlp_modulate(outs[0], outs[1], outs[2], outs[3], cls.to(cuda), mlp_c)
+    ((s_o * vs.to(cuda)).sum() + (r_o * vr.to(cuda)).sum()).backward()
+    assert_close(s_o, s_ref, rtol=1e-5, what="scaling_out")
+    assert_close(r_o, r_ref, rtol=1e-5, what="rotation_out")
+    for name, a, b in zip(("v_scaling", "v_rotation", "v_local_feat", "v_global_feat"), outs, ins):
+        assert_close(a.grad, b.grad, rtol=2e-5, what=name)
+    for (n1, p1), (_, p2) in zip(mlp_c.named_parameters(), mlp64.named_parameters()):
+        assert_close(p1.grad, p2.grad, rtol=2e-5, what="v_" + n1)

@@ -44,6 +44,9 @@ if __name__ == "__main__":
     img2 = torch.rand(B, 3, 512, 512, device=dev) * 2 - 1
     ev = lambda: torch.cuda.Event(enable_timing=True)
     for it in range(reps):
+        if os.environ.get("ADB_CUPROF") and it == reps - 1:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()     # ncu --profile-from-start off captures only this forward
         e = [ev() for _ in range(5)]
         e[0].record()
         f, pos, _ = m._encode_image(torch.cat((img1, img2), 0), None)
@@ -55,8 +58,17 @@ if __name__ == "__main__":
         r2 = m._downstream_head(2, d2, (512, 512))
         e[3].record()
         torch.cuda.synchronize()
+        if os.environ.get("ADB_CUPROF") and it == reps - 1:
+            torch.cuda.cudart().cudaProfilerStop()
         print(f"[{prec} B={B}] enc {e[0].elapsed_time(e[1]):.2f} ms  dec {e[1].elapsed_time(e[2]):.2f} ms  heads {e[2].elapsed_time(e[3]):.2f} ms  "
               f"total {e[0].elapsed_time(e[3]):.2f} ms -> {B / e[0].elapsed_time(e[3]) * 1e3:.2f} pairs/s")
+    a, b = ev(), ev()
+    forward_pair(m, img1, img2); torch.cuda.synchronize()
+    a.record()
+    for _ in range(5):
+        forward_pair(m, img1, img2)
+    b.record(); torch.cuda.synchronize()
+    print(f"[{prec} B={B}] forward_pair (two-stream heads): {a.elapsed_time(b) / 5:.2f} ms -> {B / (a.elapsed_time(b) / 5) * 1e3:.2f} pairs/s")
     if os.environ.get("ADB_STAGE"):
         _lib.TIMER = _lib.StageTimer()
         _lib.LAUNCHES.update({k: 1 for k in ("adb_gemm_bf16", "adb_layernorm", "adb_split_bf16", "adb_rope_heads",
