@@ -51,6 +51,7 @@ class AsymmetricMASt3R:
         self._sd = None          # fp32 tensors (LN params, biases, conv weights)
         self._w = {}             # name -> Split (bf16 hi/lo GEMM weights)
         self._streams = {}
+        self.concurrent = True   # run the two decoder sides / two heads on two CUDA streams
         if any(d % 64 for d in (c["enc_embed_dim"] // c["enc_num_heads"], c["dec_embed_dim"] // c["dec_num_heads"])):
             raise ValueError("head_dim must be 64")
 
@@ -232,11 +233,15 @@ class AsymmetricMASt3R:
             s1 = torch.cuda.current_stream()
             s2 = self._side_stream(f1.device)
             for i in range(self.cfg["dec_depth"]):
-                s2.wait_stream(s1)
-                with torch.cuda.stream(s2):
+                if self.concurrent:
+                    s2.wait_stream(s1)
+                    with torch.cuda.stream(s2):
+                        n2 = self._dec_block(c2, c1, pos2, pos1, f"dec_blocks2.{i}", h)
+                    n1 = self._dec_block(c1, c2, pos1, pos2, f"dec_blocks.{i}", h)
+                    s1.wait_stream(s2)
+                else:
+                    n1 = self._dec_block(c1, c2, pos1, pos2, f"dec_blocks.{i}", h)
                     n2 = self._dec_block(c2, c1, pos2, pos1, f"dec_blocks2.{i}", h)
-                n1 = self._dec_block(c1, c2, pos1, pos2, f"dec_blocks.{i}", h)
-                s1.wait_stream(s2)
                 c1, c2 = n1, n2
                 out1.append(c1)
                 out2.append(c2)
@@ -383,6 +388,8 @@ def forward_pair(model: AsymmetricMASt3R, img1, img2):
     f, pos, _ = model._encode_image(torch.cat((img1, img2), 0), None)
     (f1, f2), (p1, p2) = f.chunk(2, 0), pos.chunk(2, 0)
     d1, d2 = model._decoder(f1.contiguous(), p1.contiguous(), f2.contiguous(), p2.contiguous())
+    if not model.concurrent:
+        return model._downstream_head(1, d1, (H, W)), model._downstream_head(2, d2, (H, W))
     # the two heads are independent: overlap them on two streams
     s1 = torch.cuda.current_stream()
     s2 = model._side_stream(img1.device)

@@ -69,6 +69,19 @@ if __name__ == "__main__":
         forward_pair(m, img1, img2)
     b.record(); torch.cuda.synchronize()
     print(f"[{prec} B={B}] forward_pair (two-stream heads): {a.elapsed_time(b) / 5:.2f} ms -> {B / (a.elapsed_time(b) / 5) * 1e3:.2f} pairs/s")
+    if os.environ.get("ADB_GRAPH", "1") == "1":
+        from artdeco_b200.mast3r import GraphedForwardPair
+        ref1, ref2 = forward_pair(m, img1, img2)
+        ref_p = ref1["pts3d"].clone(); ref_q = ref2["desc"].clone()
+        g = GraphedForwardPair(m, B, 512, 512)
+        o1, o2 = g(img1, img2)
+        torch.cuda.synchronize()
+        print("graph == eager:", bool(torch.equal(o1["pts3d"], ref_p)), bool(torch.equal(o2["desc"], ref_q)))
+        a.record()
+        for _ in range(10):
+            g(img1, img2)
+        b.record(); torch.cuda.synchronize()
+        print(f"[{prec} B={B}] CUDA-graph replay: {a.elapsed_time(b) / 10:.2f} ms -> {B / (a.elapsed_time(b) / 10) * 1e3:.2f} pairs/s")
     if os.environ.get("ADB_STAGE"):
         _lib.TIMER = _lib.StageTimer()
         _lib.LAUNCHES.update({k: 1 for k in ("adb_gemm_bf16", "adb_layernorm", "adb_split_bf16", "adb_rope_heads",
