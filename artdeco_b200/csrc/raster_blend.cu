@@ -45,10 +45,15 @@ __device__ __forceinline__ bool splat_hits(const float4& A, const float4& B, con
     return (A.x + rx >= r.xlo) && (A.x - rx <= r.xhi) && (A.y + ry >= r.ylo) && (A.y - ry <= r.yhi);
 }
 
+// LEGACY = Inria conventions (ADB_CONV_INRIA): alpha <= 0.99, stop when T(1-alpha) < 1e-4 (strict), 4th channel
+// accumulates 1/z, and main_ids gets the Gaussian with the largest blending weight alpha*T per pixel (-1: none).
+template <bool LEGACY>
 __global__ void __launch_bounds__(BLOCK)
 blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* __restrict__ vals,
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
-                 float* __restrict__ colors, float* __restrict__ alphas, int32_t* __restrict__ last_ids) {
+                 float* __restrict__ colors, float* __restrict__ alphas, int32_t* __restrict__ last_ids,
+                 int32_t* __restrict__ main_ids) {
+    constexpr float MAXA = LEGACY ? ADB_MAX_ALPHA_INRIA : ADB_MAX_ALPHA;
     __shared__ float4 sA[BLOCK];
     __shared__ float4 sB[BLOCK];
     __shared__ float4 sC[BLOCK];
@@ -68,13 +73,18 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     float T = 1.0f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = 0;
+    float best_w = 0.f;
+    int best_k = -1;
     bool done = !inside;
     const int nb = (end - start + BLOCK - 1) / BLOCK;
     for (int b = 0; b < nb; ++b) {
         if (__syncthreads_count(done) >= BLOCK) break;
         const int bstart = start + b * BLOCK;
         const int idx = bstart + tid;
-        if (idx < end) gather_splat(splats, vals[idx] % n_per_cam, sA[tid], sB[tid], sC[tid]);
+        if (idx < end) {
+            gather_splat(splats, vals[idx] % n_per_cam, sA[tid], sB[tid], sC[tid]);
+            if (LEGACY) sC[tid].w = 1.0f / sC[tid].w;
+        }
         __syncthreads();
         const int bsize = min(BLOCK, end - bstart);
         if (__all_sync(FULL, done)) continue;
@@ -96,16 +106,17 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
             const float dx = A.x - px, dy = A.y - py;
             const float sigma = 0.5f * (A.z * dx * dx + B.x * dy * dy) + A.w * dx * dy;
             if (!done && sigma >= 0.f && sigma <= B.z) {
-                const float alpha = fminf(ADB_MAX_ALPHA, B.y * __expf(-sigma));
+                const float alpha = fminf(MAXA, B.y * __expf(-sigma));
                 if (alpha >= ADB_ALPHA_THRESHOLD) {
                     const float nT = T * (1.0f - alpha);
-                    if (nT <= ADB_T_EPS) {
+                    if (LEGACY ? (nT < ADB_T_EPS) : (nT <= ADB_T_EPS)) {
                         done = true;
                     } else {
                         const float w = alpha * T;
                         const float4 C = sC[t];
                         acc.x += C.x * w; acc.y += C.y * w; acc.z += C.z * w; acc.w += C.w * w;
                         cur = bstart + t;
+                        if (LEGACY && w > best_w) { best_w = w; best_k = cur; }
                         T = nT;
                     }
                 }
@@ -119,6 +130,7 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
         reinterpret_cast<float4*>(colors)[pix] = acc;
         alphas[pix] = 1.0f - T;
         last_ids[pix] = cur;
+        if (LEGACY && main_ids) main_ids[pix] = best_k >= 0 ? vals[best_k] % n_per_cam : -1;
     }
 }
 
@@ -126,13 +138,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool DIRECT>
+template <bool DIRECT, bool LEGACY>
 __global__ void __launch_bounds__(BLOCK)
 blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* __restrict__ vals,
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
                  const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
                  const float* __restrict__ v_colors, const float* __restrict__ v_alphas,
                  float* __restrict__ v_splats) {
+    constexpr float MAXA = LEGACY ? ADB_MAX_ALPHA_INRIA : ADB_MAX_ALPHA;
     __shared__ float4 sA[BLOCK];
     __shared__ float4 sB[BLOCK];
     __shared__ float4 sC[BLOCK];
@@ -180,6 +193,7 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
             const int g = vals[idx] % n_per_cam;
             sG[tid] = g;
             gather_splat(splats, g, sA[tid], sB[tid], sC[tid]);
+            if (LEGACY) sC[tid].w = 1.0f / sC[tid].w;   // v_splats slot 9 is then dL/d(1/z)
         }
         if (!DIRECT) {
             float4* z = reinterpret_cast<float4*>(sAcc[tid]);
@@ -209,7 +223,7 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
                 float vis = 0.f, alpha = 0.f;
                 if (valid) {
                     vis = __expf(-sigma);
-                    alpha = fminf(ADB_MAX_ALPHA, B.y * vis);
+                    alpha = fminf(MAXA, B.y * vis);
                     valid = alpha >= ADB_ALPHA_THRESHOLD;
                 }
                 if (!__any_sync(FULL, valid)) continue;
@@ -231,7 +245,7 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
                     v[6] = fac * vo.x; v[7] = fac * vo.y; v[8] = fac * vo.z; v[9] = fac * vo.w;
                     // d(alpha)/d(sigma) path is cut where alpha was clamped to 0.999
                     const float ov = B.y * vis;
-                    const float v_sigma = ov <= ADB_MAX_ALPHA ? -ov * v_alpha : 0.f;
+                    const float v_sigma = ov <= MAXA ? -ov * v_alpha : 0.f;
                     // raw moments of v_sigma about the splat centre; project_bwd turns them into
                     // v_mean2d / v_conic / v_opacity once per Gaussian instead of once per pair
                     v[5] = v_sigma;
@@ -294,16 +308,57 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
 
 }  // namespace
 
+static int blend_fwd_impl(bool legacy, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                          const int32_t* tile_offsets, float* colors, float* alphas, int32_t* last_ids,
+                          int32_t* main_ids, cudaStream_t stream) {
+    ADB_REQUIRE(W > 0 && H > 0 && n_per_cam >= 0, "adb_raster_blend_fwd: bad sizes");
+    ADB_REQUIRE(tile_offsets && colors && alphas && last_ids, "adb_raster_blend_fwd: null pointer");
+    dim3 grid(adb_cdiv(W, ADB_TILE), adb_cdiv(H, ADB_TILE));
+    if (legacy)
+        blend_fwd_kernel<true><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
+                                                          colors, alphas, last_ids, main_ids);
+    else
+        blend_fwd_kernel<false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
+                                                           colors, alphas, last_ids, nullptr);
+    ADB_CHECK_LAUNCH("blend_fwd_kernel");
+    return ADB_OK;
+}
+
 // `vals` are the sorted values (cam*N + gaussian); n_per_cam = N.  colors [H,W,4], alphas [H,W], last_ids [H,W].
 ADB_API int adb_raster_blend_fwd(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
                                  const int32_t* tile_offsets, float* colors, float* alphas, int32_t* last_ids,
                                  cudaStream_t stream) {
-    ADB_REQUIRE(W > 0 && H > 0 && n_per_cam >= 0, "adb_raster_blend_fwd: bad sizes");
-    ADB_REQUIRE(tile_offsets && colors && alphas && last_ids, "adb_raster_blend_fwd: null pointer");
+    return blend_fwd_impl(false, W, H, n_per_cam, splats, vals_sorted, tile_offsets, colors, alphas, last_ids, nullptr,
+                          stream);
+}
+
+// Legacy (Inria) blending: colors[...,3] = sum alpha*T/z (inverse depth); main_ids [H,W] may be NULL.
+ADB_API int adb_raster_blend_fwd_legacy(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                                        const int32_t* tile_offsets, float* colors, float* alphas, int32_t* last_ids,
+                                        int32_t* main_ids, cudaStream_t stream) {
+    return blend_fwd_impl(true, W, H, n_per_cam, splats, vals_sorted, tile_offsets, colors, alphas, last_ids, main_ids,
+                          stream);
+}
+
+static int blend_bwd_impl(bool legacy, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                          const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
+                          const float* v_colors, const float* v_alphas, float* v_splats, cudaStream_t stream) {
+    ADB_REQUIRE(W > 0 && H > 0 && n_per_cam >= 0, "adb_raster_blend_bwd: bad sizes");
+    ADB_REQUIRE(tile_offsets && alphas && last_ids && v_colors && v_alphas, "adb_raster_blend_bwd: null pointer");
+    if (n_per_cam == 0) return ADB_OK;
+    ADB_REQUIRE(v_splats, "adb_raster_blend_bwd: null v_splats");
     dim3 grid(adb_cdiv(W, ADB_TILE), adb_cdiv(H, ADB_TILE));
-    blend_fwd_kernel<<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1), colors,
-                                                alphas, last_ids);
-    ADB_CHECK_LAUNCH("blend_fwd_kernel");
+    static const int mode = getenv("ADB_BWD_MODE") ? atoi(getenv("ADB_BWD_MODE")) : 0;
+    if (legacy)
+        blend_bwd_kernel<false, true><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, n_per_cam,
+                                                                 alphas, last_ids, v_colors, v_alphas, v_splats);
+    else if (mode == 1)
+        blend_bwd_kernel<true, false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, n_per_cam,
+                                                                 alphas, last_ids, v_colors, v_alphas, v_splats);
+    else
+        blend_bwd_kernel<false, false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, n_per_cam,
+                                                                  alphas, last_ids, v_colors, v_alphas, v_splats);
+    ADB_CHECK_LAUNCH("blend_bwd_kernel");
     return ADB_OK;
 }
 
@@ -312,18 +367,16 @@ ADB_API int adb_raster_blend_bwd(int W, int H, int n_per_cam, const float* splat
                                  const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
                                  const float* v_colors, const float* v_alphas, float* v_splats,
                                  cudaStream_t stream) {
-    ADB_REQUIRE(W > 0 && H > 0 && n_per_cam >= 0, "adb_raster_blend_bwd: bad sizes");
-    ADB_REQUIRE(tile_offsets && alphas && last_ids && v_colors && v_alphas, "adb_raster_blend_bwd: null pointer");
-    if (n_per_cam == 0) return ADB_OK;
-    ADB_REQUIRE(v_splats, "adb_raster_blend_bwd: null v_splats");
-    dim3 grid(adb_cdiv(W, ADB_TILE), adb_cdiv(H, ADB_TILE));
-    static const int mode = getenv("ADB_BWD_MODE") ? atoi(getenv("ADB_BWD_MODE")) : 0;
-    if (mode == 1)
-        blend_bwd_kernel<true><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, n_per_cam, alphas,
-                                                          last_ids, v_colors, v_alphas, v_splats);
-    else
-        blend_bwd_kernel<false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, n_per_cam, alphas,
-                                                           last_ids, v_colors, v_alphas, v_splats);
-    ADB_CHECK_LAUNCH("blend_bwd_kernel");
-    return ADB_OK;
+    return blend_bwd_impl(false, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
+                          v_alphas, v_splats, stream);
+}
+
+// Legacy (Inria) conventions; v_colors[...,3] is the upstream gradient of the inverse-depth channel and v_splats slot 9
+// receives dL/d(1/z) per Gaussian (the caller multiplies by -1/z^2 before adb_raster_project_bwd).
+ADB_API int adb_raster_blend_bwd_legacy(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                                        const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
+                                        const float* v_colors, const float* v_alphas, float* v_splats,
+                                        cudaStream_t stream) {
+    return blend_bwd_impl(true, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
+                          v_alphas, v_splats, stream);
 }

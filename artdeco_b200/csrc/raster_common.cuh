@@ -22,6 +22,13 @@
 #define ADB_ALPHA_THRESHOLD (1.0f / 255.0f)
 #define ADB_MAX_ALPHA 0.999f
 #define ADB_T_EPS 1e-4f
+// Rendering conventions.  GSPLAT: what the live path uses (h3dgsv3.py:664-680).  INRIA: the legacy
+// diff_gaussian_rasterization contract of the web viewer (Reconstruct/webviewer/scene_models.py:559-605):
+// radius ceil(3 sqrt(lambda_max)) with a 0.1 floor under the root, tile rectangle on pixel-index coordinates
+// ((int)((p-r)/16) .. (int)((p+r+15)/16)), alpha <= 0.99, stop when T(1-alpha) < 1e-4, 4th channel = sum alpha T / z.
+#define ADB_CONV_GSPLAT 0
+#define ADB_CONV_INRIA 1
+#define ADB_MAX_ALPHA_INRIA 0.99f
 
 struct AdbCam {
     const float* viewmat;  // device, 16
@@ -29,7 +36,30 @@ struct AdbCam {
     const float* campos;   // device, 3 (may be null when no SH)
     int W, H;
     float eps2d, near_plane, far_plane, radius_clip;
+    int convention;  // ADB_CONV_*
 };
+
+// Tile rectangle [x0,x1) x [y0,y1) a splat touches.  The GSPLAT arithmetic must stay exactly as written: it feeds the
+// bit-exact tile keys (oracle/raster_oracle.c tile_bounds).
+__device__ __forceinline__ void adb_tile_rect(float u, float v, int rx_i, int ry_i, int W, int H, int convention,
+                                              int& x0, int& x1, int& y0, int& y1) {
+    const int tw = (W + ADB_TILE - 1) / ADB_TILE, th = (H + ADB_TILE - 1) / ADB_TILE;
+    if (convention == ADB_CONV_INRIA) {
+        const float px = u - 0.5f, py = v - 0.5f;  // Inria pixel-index coordinates (centres at integers)
+        const float rx = (float)rx_i, ry = (float)ry_i, t = (float)ADB_TILE;
+        x0 = min(tw, max(0, (int)((px - rx) / t)));
+        x1 = min(tw, max(0, (int)((px + rx + (t - 1.f)) / t)));
+        y0 = min(th, max(0, (int)((py - ry) / t)));
+        y1 = min(th, max(0, (int)((py + ry + (t - 1.f)) / t)));
+        return;
+    }
+    float mx = u / (float)ADB_TILE, my = v / (float)ADB_TILE;
+    float trx = (float)rx_i / (float)ADB_TILE, try_ = (float)ry_i / (float)ADB_TILE;
+    x0 = (int)fminf(fmaxf(0.f, floorf(mx - trx)), (float)tw);
+    x1 = (int)fminf(fmaxf(0.f, ceilf(mx + trx)), (float)tw);
+    y0 = (int)fminf(fmaxf(0.f, floorf(my - try_)), (float)th);
+    y1 = (int)fminf(fmaxf(0.f, ceilf(my + try_)), (float)th);
+}
 
 __host__ __device__ inline int adb_tile_bits(int W, int H) {
     int tw = (W + ADB_TILE - 1) / ADB_TILE, th = (H + ADB_TILE - 1) / ADB_TILE;

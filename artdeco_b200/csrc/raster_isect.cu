@@ -20,7 +20,7 @@ struct ToI64 {
 
 __global__ void __launch_bounds__(256)
 isect_emit_kernel(int N, const int32_t* __restrict__ radii, const float* __restrict__ splats,
-                  const int64_t* __restrict__ cum_tiles, int W, int H, int cam_id, int tile_bits,
+                  const int64_t* __restrict__ cum_tiles, int W, int H, int cam_id, int tile_bits, int convention,
                   int64_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -28,14 +28,11 @@ isect_emit_kernel(int N, const int32_t* __restrict__ radii, const float* __restr
     if (r.x <= 0 && r.y <= 0) return;
     const float4 rec0 = reinterpret_cast<const float4*>(splats + (size_t)i * ADB_SPLAT_STRIDE)[0];
     const float depth = splats[(size_t)i * ADB_SPLAT_STRIDE + 11];
-    const int tw = (W + ADB_TILE - 1) / ADB_TILE, th = (H + ADB_TILE - 1) / ADB_TILE;
-    float mx = rec0.x / (float)ADB_TILE, my = rec0.y / (float)ADB_TILE;
-    float trx = (float)r.x / (float)ADB_TILE, try_ = (float)r.y / (float)ADB_TILE;
-    int x0 = (int)fminf(fmaxf(0.f, floorf(mx - trx)), (float)tw);
-    int x1 = (int)fminf(fmaxf(0.f, ceilf(mx + trx)), (float)tw);
-    int y0 = (int)fminf(fmaxf(0.f, floorf(my - try_)), (float)th);
-    int y1 = (int)fminf(fmaxf(0.f, ceilf(my + try_)), (float)th);
+    const int tw = (W + ADB_TILE - 1) / ADB_TILE;
+    int x0, x1, y0, y1;
+    adb_tile_rect(rec0.x, rec0.y, r.x, r.y, W, H, convention, x0, x1, y0, y1);
     int64_t o = (i == 0) ? 0 : cum_tiles[i - 1];
+    if (convention != ADB_CONV_GSPLAT && cum_tiles[i] == o) return;  // kept its radius but was given no tiles
     const uint64_t hi = (uint64_t)cam_id << (32 + tile_bits);
     const uint64_t dbits = (uint64_t)__float_as_uint(depth);
     const int32_t val = cam_id * N + i;
@@ -94,16 +91,28 @@ ADB_API int adb_raster_isect_scan(int N, const int32_t* tiles_per_gauss, int64_t
     return ADB_OK;
 }
 
-ADB_API int adb_raster_isect_emit(int N, const int32_t* radii, const float* splats, const int64_t* cum_tiles,
-                                  int W, int H, int cam_id, int n_cams, int64_t* keys, int32_t* vals,
-                                  cudaStream_t stream) {
+static int isect_emit_impl(int convention, int N, const int32_t* radii, const float* splats, const int64_t* cum_tiles,
+                           int W, int H, int cam_id, int n_cams, int64_t* keys, int32_t* vals, cudaStream_t stream) {
     ADB_REQUIRE(N >= 0 && W > 0 && H > 0 && cam_id >= 0 && n_cams > cam_id, "adb_raster_isect_emit: bad sizes");
     if (N == 0) return ADB_OK;
     ADB_REQUIRE(radii && splats && cum_tiles && keys && vals, "adb_raster_isect_emit: null pointer");
     isect_emit_kernel<<<adb_cdiv(N, 256), 256, 0, stream>>>(N, radii, splats, cum_tiles, W, H, cam_id,
-                                                           adb_tile_bits(W, H), keys, vals);
+                                                           adb_tile_bits(W, H), convention, keys, vals);
     ADB_CHECK_LAUNCH("isect_emit_kernel");
     return ADB_OK;
+}
+
+ADB_API int adb_raster_isect_emit(int N, const int32_t* radii, const float* splats, const int64_t* cum_tiles,
+                                  int W, int H, int cam_id, int n_cams, int64_t* keys, int32_t* vals,
+                                  cudaStream_t stream) {
+    return isect_emit_impl(ADB_CONV_GSPLAT, N, radii, splats, cum_tiles, W, H, cam_id, n_cams, keys, vals, stream);
+}
+
+// Legacy (Inria) tile rectangle; everything else (key layout, emission order) as above.
+ADB_API int adb_raster_isect_emit_legacy(int N, const int32_t* radii, const float* splats, const int64_t* cum_tiles,
+                                         int W, int H, int cam_id, int n_cams, int64_t* keys, int32_t* vals,
+                                         cudaStream_t stream) {
+    return isect_emit_impl(ADB_CONV_INRIA, N, radii, splats, cum_tiles, W, H, cam_id, n_cams, keys, vals, stream);
 }
 
 ADB_API int adb_raster_sort_workspace_bytes(long long n_isect, size_t* bytes) {

@@ -57,7 +57,7 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
     const float fx = cam.K[0], fy = cam.K[4], cx = cam.K[2], cy = cam.K[5];
     const float m0 = means[3 * i], m1 = means[3 * i + 1], m2 = means[3 * i + 2];
 
-    int rx_i = 0, ry_i = 0, count = 0;
+    int rx_i = 0, ry_i = 0, count = 0, cull_rx = 0, cull_ry = 0;
     float u = 0.f, v = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, lg = 0.f;
     const float x = R[0] * m0 + R[1] * m1 + R[2] * m2 + t[0];
     const float y = R[3] * m0 + R[4] * m1 + R[5] * m2 + t[1];
@@ -106,6 +106,36 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
         a = a + cam.eps2d;
         c = c + cam.eps2d;
         float det = a * c - b * b;
+        if (cam.convention == ADB_CONV_INRIA) {
+            ok = det > 0.f;
+            if (ok) {
+                u = fx * x * rz + cx;
+                v = fy * y * rz + cy;
+                const float mid = 0.5f * (a + c);
+                const float lam1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+                const int rI = (int)fminf(ceilf(3.0f * sqrtf(lam1)), 1.0e9f);
+                int x0, x1, y0, y1;
+                adb_tile_rect(u, v, rI, rI, cam.W, cam.H, ADB_CONV_INRIA, x0, x1, y0, y1);
+                count = (x1 - x0) * (y1 - y0);
+                ok = count > 0;          // Inria leaves radii = 0 when no tile is touched
+                if (ok) {
+                    rx_i = ry_i = rI;
+                    ca = c / det; cb = -b / det; cc = a / det;
+                    if (opacity < ADB_ALPHA_THRESHOLD) {
+                        // alpha can never reach 1/255: keeps its radius (visibility filter) and a record (so the
+                        // backward reads defined values) but emits no keys
+                        count = 0;
+                    } else {
+                        // conservative extent for the blend kernels' block-level culling (alpha < 1/255 outside it)
+                        lg = adb_det_logf(opacity / ADB_ALPHA_THRESHOLD);
+                        const float ext = fminf(3.33f, sqrtf(2.0f * lg));
+                        const float r1 = ext * sqrtf(lam1);
+                        cull_rx = (int)fminf(ceilf(fminf(ext * sqrtf(a), r1)), 65535.f);
+                        cull_ry = (int)fminf(ceilf(fminf(ext * sqrtf(c), r1)), 65535.f);
+                    }
+                }
+            }
+        } else {
         ok = det > 0.f && !(opacity < ADB_ALPHA_THRESHOLD);
         if (ok) {
             u = fx * x * rz + cx;
@@ -122,17 +152,14 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
                  !(u + rx <= 0.f || u - rx >= W || v + ry <= 0.f || v - ry >= H);
             if (ok) {
                 rx_i = (int)rx; ry_i = (int)ry;
+                cull_rx = rx_i; cull_ry = ry_i;
                 ca = c / det; cb = -b / det; cc = a / det;
                 // tile count (same arithmetic as the emit kernel and the oracle's tile_bounds)
-                int tw = (cam.W + ADB_TILE - 1) / ADB_TILE, th = (cam.H + ADB_TILE - 1) / ADB_TILE;
-                float mx = u / (float)ADB_TILE, my = v / (float)ADB_TILE;
-                float trx = (float)rx_i / (float)ADB_TILE, try_ = (float)ry_i / (float)ADB_TILE;
-                int x0 = (int)fminf(fmaxf(0.f, floorf(mx - trx)), (float)tw);
-                int x1 = (int)fminf(fmaxf(0.f, ceilf(mx + trx)), (float)tw);
-                int y0 = (int)fminf(fmaxf(0.f, floorf(my - try_)), (float)th);
-                int y1 = (int)fminf(fmaxf(0.f, ceilf(my + try_)), (float)th);
+                int x0, x1, y0, y1;
+                adb_tile_rect(u, v, rx_i, ry_i, cam.W, cam.H, ADB_CONV_GSPLAT, x0, x1, y0, y1);
                 count = (x1 - x0) * (y1 - y0);
             }
+        }
         }
     }
     reinterpret_cast<int2*>(radii)[i] = make_int2(rx_i, ry_i);
@@ -161,7 +188,7 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
     float4* out = reinterpret_cast<float4*>(splats + (size_t)i * ADB_SPLAT_STRIDE);
     // sigma <= ln(255*opacity) <=> alpha >= 1/255; the margin keeps the pre-test a strict superset of the exact test
     const float sigma_max = lg + 0.02f;
-    const unsigned packed_radii = (unsigned)min(rx_i, 65535) | ((unsigned)min(ry_i, 65535) << 16);
+    const unsigned packed_radii = (unsigned)min(cull_rx, 65535) | ((unsigned)min(cull_ry, 65535) << 16);
     out[0] = make_float4(u, v, ca, cb);
     out[1] = make_float4(cc, opacity, sigma_max, __uint_as_float(packed_radii));
     out[2] = make_float4(r, g, bl, z);
@@ -170,20 +197,40 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
 }  // namespace
 
 // One camera.  `sh` may be NULL (then rgb = 0 and campos is ignored).  viewmat/K/campos are DEVICE pointers.
-ADB_API int adb_raster_project_fwd(int N, const float* means, const float* quats, const float* scales,
-                                   const float* opacities, const float* sh, int sh_degree,
-                                   const float* viewmat, const float* K, const float* campos, int W, int H,
-                                   float eps2d, float near_plane, float far_plane, float radius_clip,
-                                   int32_t* radii, float* splats, int32_t* tiles_per_gauss, cudaStream_t stream) {
+static int project_fwd_impl(int convention, int N, const float* means, const float* quats, const float* scales,
+                            const float* opacities, const float* sh, int sh_degree,
+                            const float* viewmat, const float* K, const float* campos, int W, int H,
+                            float eps2d, float near_plane, float far_plane, float radius_clip,
+                            int32_t* radii, float* splats, int32_t* tiles_per_gauss, cudaStream_t stream) {
     ADB_REQUIRE(N >= 0 && W > 0 && H > 0, "adb_raster_project_fwd: bad sizes");
     if (N == 0) return ADB_OK;
     ADB_REQUIRE(means && quats && scales && opacities && viewmat && K && radii && splats && tiles_per_gauss,
                 "adb_raster_project_fwd: null pointer");
     ADB_REQUIRE(!sh || campos, "adb_raster_project_fwd: sh needs campos");
     ADB_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "adb_raster_project_fwd: sh_degree must be 0..3");
-    AdbCam cam{viewmat, K, campos, W, H, eps2d, near_plane, far_plane, radius_clip};
+    AdbCam cam{viewmat, K, campos, W, H, eps2d, near_plane, far_plane, radius_clip, convention};
     project_fwd_kernel<<<adb_cdiv(N, 256), 256, 0, stream>>>(N, means, quats, scales, opacities, sh, sh_degree, cam,
                                                             radii, splats, tiles_per_gauss);
     ADB_CHECK_LAUNCH("project_fwd_kernel");
     return ADB_OK;
+}
+
+ADB_API int adb_raster_project_fwd(int N, const float* means, const float* quats, const float* scales,
+                                   const float* opacities, const float* sh, int sh_degree,
+                                   const float* viewmat, const float* K, const float* campos, int W, int H,
+                                   float eps2d, float near_plane, float far_plane, float radius_clip,
+                                   int32_t* radii, float* splats, int32_t* tiles_per_gauss, cudaStream_t stream) {
+    return project_fwd_impl(ADB_CONV_GSPLAT, N, means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H,
+                            eps2d, near_plane, far_plane, radius_clip, radii, splats, tiles_per_gauss, stream);
+}
+
+// Legacy (Inria / diff_gaussian_rasterization) conventions: radii[:,0] == radii[:,1] == ceil(3 sqrt(lambda_max)); the
+// caller passes eps2d = 0.3 and near_plane = 0.2.  Same record layout (slot 11 stays the camera-space depth z).
+ADB_API int adb_raster_project_fwd_legacy(int N, const float* means, const float* quats, const float* scales,
+                                          const float* opacities, const float* sh, int sh_degree,
+                                          const float* viewmat, const float* K, const float* campos, int W, int H,
+                                          float eps2d, float near_plane, float far_plane,
+                                          int32_t* radii, float* splats, int32_t* tiles_per_gauss, cudaStream_t stream) {
+    return project_fwd_impl(ADB_CONV_INRIA, N, means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H,
+                            eps2d, near_plane, far_plane, 0.f, radii, splats, tiles_per_gauss, stream);
 }

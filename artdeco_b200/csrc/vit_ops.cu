@@ -345,3 +345,46 @@ ADB_API int adb_im2col_patch16(int B, int H, int W, const float* img, void* hi, 
     ADB_CHECK_LAUNCH("im2col_patch_kernel");
     return ADB_OK;
 }
+
+// ---- curope.rope_2d: in-place RoPE2D on tokens [B,N,H,D] (VSLAM/thirdparty/mast3r/dust3r/croco/models/curope/
+// kernels.cu:18-108, curope.cpp:49-68).  One head = [u_Y (Q) | v_Y (Q) | u_X (Q) | v_X (Q)], Q = D/4;
+// inv_freq_i = F0 / base^(i/Q); (u,v) <- (u c - v s, v c + u s) with the angle pos_{y|x} * inv_freq_i.
+// One CTA per token: the D/2 (cos,sin) pairs are computed once (precise powf/sincosf; the reference build uses
+// --use_fast_math intrinsics, its PyTorch fallback pos_embed.py:112-159 is exact) and reused by all H heads.
+namespace {
+__global__ void __launch_bounds__(256)
+rope2d_inplace_kernel(float* __restrict__ tok, const long long* __restrict__ pos, int N, int H, int D,
+                      long long sb, long long sn, float base, float F0) {
+    const int b = blockIdx.x / N, n = blockIdx.x % N;
+    const int half = D / 2, Q = D / 4;
+    const int p = threadIdx.x % half;          // pair index: [0,Q) -> Y, [Q,2Q) -> X
+    const int hl = threadIdx.x / half, hstep = blockDim.x / half;
+    const int X = p >= Q, i = p - X * Q;
+    const float ang = (float)pos[((long long)b * N + n) * 2 + X] * (F0 / powf(base, (float)i / (float)Q));
+    float s, c;
+    sincosf(ang, &s, &c);
+    float* t = tok + b * sb + n * sn + X * half + i;
+    for (int h = hl; h < H; h += hstep) {
+        float* q = t + (long long)h * D;
+        const float u = q[0], v = q[Q];
+        q[0] = u * c - v * s;
+        q[Q] = v * c + u * s;
+    }
+}
+}  // namespace
+
+ADB_API int adb_rope2d_inplace(int B, int N, int H, int D, long long stride_b, long long stride_n, float* tokens,
+                               const long long* positions, float base, float F0, cudaStream_t stream) {
+    ADB_REQUIRE(B >= 0 && N >= 0 && H > 0 && D > 0, "adb_rope2d_inplace: bad sizes");
+    ADB_REQUIRE(D % 4 == 0 && D <= 512, "adb_rope2d_inplace: token dim must be a multiple of 4 (and <= 512)");
+    if ((long long)B * N == 0) return ADB_OK;
+    ADB_REQUIRE(tokens && positions, "adb_rope2d_inplace: null pointer");
+    const int half = D / 2;
+    int hy = 256 / half;
+    if (hy < 1) hy = 1;
+    if (hy > H) hy = H;
+    rope2d_inplace_kernel<<<(unsigned)((long long)B * N), half * hy, 0, stream>>>(tokens, positions, N, H, D, stride_b,
+                                                                                stride_n, base, F0);
+    ADB_CHECK_LAUNCH("rope2d_inplace_kernel");
+    return ADB_OK;
+}

@@ -2,3 +2,4 @@
 from . import ops  # noqa: F401  (registers the C signatures)
 from .model import FULL_CFG, AsymmetricMASt3R, forward_pair  # noqa: F401
 from .graph import GraphedForwardPair  # noqa: F401,E402
+from . import curope, wrappers  # noqa: F401,E402

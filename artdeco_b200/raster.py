@@ -30,6 +30,12 @@ _lib.register("adb_raster_blend_bwd", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp
 _lib.register("adb_raster_project_bwd", [i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32,
                                          vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 
+_lib.register("adb_raster_project_fwd_legacy", [i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32,
+                                                vp, vp, vp, vp])
+_lib.register("adb_raster_isect_emit_legacy", [i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp])
+_lib.register("adb_raster_blend_fwd_legacy", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp])
+_lib.register("adb_raster_blend_bwd_legacy", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+
 TILE = 16
 SPLAT_STRIDE = 12
 
@@ -51,20 +57,27 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
-def project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H, eps2d, near, far, radius_clip):
-    """Projection + SH + tile counts for one camera.  Returns radii[N,2] i32, splats[N,12], tiles_per_gauss[N]."""
+def project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H, eps2d, near, far, radius_clip,
+            legacy=False):
+    """Projection + SH + tile counts for one camera.  Returns radii[N,2] i32, splats[N,12], tiles_per_gauss[N].
+    ``legacy``: Inria conventions (see include/artdeco_b200.h, adb_raster_project_fwd_legacy)."""
     N = means.shape[0]
     dev = means.device
     radii = torch.empty(N, 2, dtype=torch.int32, device=dev)
     splats = torch.empty(N, SPLAT_STRIDE, dtype=torch.float32, device=dev)
     tpg = torch.empty(N, dtype=torch.int32, device=dev)
+    if legacy:
+        _lib.call("adb_raster_project_fwd_legacy", N, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales),
+                  _lib.ptr(opacities), _lib.ptr(sh), int(sh_degree), _lib.ptr(viewmat), _lib.ptr(K), _lib.ptr(campos),
+                  W, H, eps2d, near, far, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), _lib.stream())
+        return radii, splats, tpg
     _lib.call("adb_raster_project_fwd", N, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
               _lib.ptr(sh), int(sh_degree), _lib.ptr(viewmat), _lib.ptr(K), _lib.ptr(campos), W, H, eps2d, near, far,
               radius_clip, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), _lib.stream())
     return radii, splats, tpg
 
 
-def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True):
+def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=False):
     """Tile keys/values (sorted), tile offsets [T+1].  One host sync (reads the intersection count)."""
     N = radii.shape[0]
     dev = radii.device
@@ -83,7 +96,7 @@ def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True):
     keys_a = torch.empty(max(n_isect, 1), dtype=torch.int64, device=dev)
     vals_a = torch.empty(max(n_isect, 1), dtype=torch.int32, device=dev)
     if n_isect > 0:
-        _lib.call("adb_raster_isect_emit", N, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(cum), W, H, cam_id, n_cams,
+        _lib.call("adb_raster_isect_emit_legacy" if legacy else "adb_raster_isect_emit", N, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(cum), W, H, cam_id, n_cams,
                   _lib.ptr(keys_a), _lib.ptr(vals_a), _lib.stream())
     keys, vals = keys_a, vals_a
     if sort and n_isect > 0:
@@ -99,19 +112,26 @@ def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True):
     return keys[:n_isect], vals[:n_isect], offsets, n_isect
 
 
-def blend_forward(W, H, N, splats, vals, offsets):
+def blend_forward(W, H, N, splats, vals, offsets, legacy=False):
+    """``legacy`` returns a 4th tensor main_ids[H,W] and accumulates 1/z in colors[...,3]."""
     dev = splats.device
     colors = torch.empty(H, W, 4, dtype=torch.float32, device=dev)
     alphas = torch.empty(H, W, dtype=torch.float32, device=dev)
     last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
+    if legacy:
+        main_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
+        _lib.call("adb_raster_blend_fwd_legacy", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
+                  _lib.ptr(offsets), _lib.ptr(colors), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(main_ids),
+                  _lib.stream())
+        return colors, alphas, last_ids, main_ids
     _lib.call("adb_raster_blend_fwd", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
               _lib.ptr(offsets), _lib.ptr(colors), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.stream())
     return colors, alphas, last_ids
 
 
-def blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas):
+def blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas, legacy=False):
     v_splats = torch.zeros(N, SPLAT_STRIDE, dtype=torch.float32, device=splats.device)
-    _lib.call("adb_raster_blend_bwd", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
+    _lib.call("adb_raster_blend_bwd_legacy" if legacy else "adb_raster_blend_bwd", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
               _lib.ptr(offsets), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(v_colors), _lib.ptr(v_alphas),
               _lib.ptr(v_splats), _lib.stream())
     return v_splats

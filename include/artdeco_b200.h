@@ -71,6 +71,27 @@ int adb_raster_project_bwd(int N, const float* means, const float* quats, const 
                            float* v_scales, float* v_opac, float* v_sh, float* v_viewmat /*[16] +=*/,
                            float* v_campos /*[3] +=*/, adb_stream_t stream);
 
+/* ---- legacy (Inria / diff_gaussian_rasterization) conventions: GaussianRasterizer / rasterize_gaussians as called at
+ * Reconstruct/webviewer/scene_models.py:559-605 (the fork itself is not vendored, so the constants are
+ * the published Inria ones: radius ceil(3 sqrt(lambda_max)), +0.3 px^2 low-pass (pass eps2d = 0.3), near 0.2, alpha <= 0.99,
+ * stop at T(1-alpha) < 1e-4, tile rectangle (int)((p-r)/16)..(int)((p+r+15)/16) on pixel-index coordinates).
+ * Same buffers and key layout as the gsplat-convention entry points above; scan / sort / tile_offsets / project_bwd are shared. */
+int adb_raster_project_fwd_legacy(int N, const float* means, const float* quats, const float* scales,
+                                  const float* opacities, const float* sh, int sh_degree, const float* viewmat,
+                                  const float* K, const float* campos, int W, int H, float eps2d, float near_plane,
+                                  float far_plane, int32_t* radii /*[N,2], both = Inria radius*/, float* splats,
+                                  int32_t* tiles_per_gauss, adb_stream_t stream);
+int adb_raster_isect_emit_legacy(int N, const int32_t* radii, const float* splats, const int64_t* cum_tiles, int W, int H,
+                                 int cam_id, int n_cams, int64_t* keys, int32_t* vals, adb_stream_t stream);
+int adb_raster_blend_fwd_legacy(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                                const int32_t* tile_offsets, float* colors /*[H,W,4]: rgb, sum alpha*T/z*/, float* alphas,
+                                int32_t* last_ids, int32_t* main_ids /*[H,W] argmax alpha*T, -1 none; may be NULL*/,
+                                adb_stream_t stream);
+int adb_raster_blend_bwd_legacy(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                                const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
+                                const float* v_colors, const float* v_alphas, float* v_splats /*slot 9 = dL/d(1/z)*/,
+                                adb_stream_t stream);
+
 /* ---- covariance-modulation MLP (SceneModel.render, Reconstruct/scene/scene_models/h3dgsv3.py:656-662; mlp_cov :173-177) ----
  * x = cat(global_feat[cls_id], local_feat); o = W2 relu(W1 x + b1) + b2; scale_out = scaling*sigmoid(o[:3]);
  * rot_out = normalize(rotation*o[3:]).  D = Fg+Fl in {32,64}.  Backward ACCUMULATES v_global_feat, v_W1, v_b1, v_W2, v_b2. */
@@ -142,6 +163,11 @@ int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, const void* 
 int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
                   void* y_hi, void* y_lo, adb_stream_t stream);
 int adb_split_bf16(long long n, const float* x, void* hi, void* lo, adb_stream_t stream);
+/* curope.rope_2d(tokens[B,N,H,D] fp32 IN PLACE, positions[B,N,2] int64 (y,x), base, F0) — curope.cpp:49-68, kernels.cu:18-108.
+ * tokens: stride(3) == 1 and stride(2) == D as the reference checks (kernels.cu:91); stride_b / stride_n in elements.
+ * F0 = -1 applies the inverse rotation (the reference's backward, curope2d.py:25-29). */
+int adb_rope2d_inplace(int B, int N, int H, int D, long long stride_b, long long stride_n, float* tokens,
+                       const long long* positions, float base, float F0, adb_stream_t stream);
 int adb_rope_heads(int B, int N, int h, long long ld, int col0, const float* x, const long long* pos /*[B,N,2] (y,x)*/,
                    const float* table /*[n_pos][16][2] (cos,sin)*/, int n_pos, int mode, int Npad, void* hi, void* lo,
                    adb_stream_t stream);

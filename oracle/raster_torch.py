@@ -110,8 +110,9 @@ def sh_colors(means, campos, sh, degree):
     return torch.clamp_min(torch.einsum("nk,nkc->nc", basis, sh) + 0.5, 0.0)
 
 
-def isect_and_sort(radii, means2d, depths, W, H, cam_id=0, n_cams=1):
-    """Returns sorted keys (int64), sorted gaussian ids (int32), tile offsets [T_h*T_w] (int32)."""
+def isect_and_sort(radii, means2d, depths, W, H, cam_id=0, n_cams=1, rect_fn=None):
+    """Returns sorted keys (int64), sorted gaussian ids (int32), tile offsets [T_h*T_w] (int32).
+    ``rect_fn(i, tw, th) -> (x0, x1, y0, y1) or None`` overrides the gsplat tile rectangle (oracle/legacy_torch.py)."""
     tw, th = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     tile_bits = (tw * th).bit_length()
     keys, vals = [], []
@@ -123,10 +124,16 @@ def isect_and_sort(radii, means2d, depths, W, H, cam_id=0, n_cams=1):
         mx, my = float(means2d[i, 0]) / TILE, float(means2d[i, 1]) / TILE
         # float32 arithmetic like the kernels
         f = lambda v: float(torch.tensor(v, dtype=torch.float32))
-        x0 = min(max(0, int(math.floor(f(f(mx) - f(rx / TILE))))), tw)
-        x1 = min(max(0, int(math.ceil(f(f(mx) + f(rx / TILE))))), tw)
-        y0 = min(max(0, int(math.floor(f(f(my) - f(ry / TILE))))), th)
-        y1 = min(max(0, int(math.ceil(f(f(my) + f(ry / TILE))))), th)
+        if rect_fn is not None:
+            rect = rect_fn(i, tw, th)
+            if rect is None:
+                continue
+            x0, x1, y0, y1 = rect
+        else:
+            x0 = min(max(0, int(math.floor(f(f(mx) - f(rx / TILE))))), tw)
+            x1 = min(max(0, int(math.ceil(f(f(mx) + f(rx / TILE))))), tw)
+            y0 = min(max(0, int(math.floor(f(f(my) - f(ry / TILE))))), th)
+            y1 = min(max(0, int(math.ceil(f(f(my) + f(ry / TILE))))), th)
         for ty in range(y0, y1):
             for tx in range(x0, x1):
                 keys.append((cam_id << (32 + tile_bits)) | ((ty * tw + tx) << 32) | int(d_bits[i]))
@@ -141,8 +148,10 @@ def isect_and_sort(radii, means2d, depths, W, H, cam_id=0, n_cams=1):
     return keys_t, vals_t, offsets
 
 
-def blend(means2d, conics, opacities, feats, vals, offsets, W, H):
-    """feats [N,CHN]; returns out[H,W,CHN], alpha[H,W], last_ids[H,W] (index into the sorted list)."""
+def blend(means2d, conics, opacities, feats, vals, offsets, W, H, max_alpha=MAX_ALPHA, strict_stop=False, main_ids=None):
+    """feats [N,CHN]; returns out[H,W,CHN], alpha[H,W], last_ids[H,W] (index into the sorted list).
+    ``max_alpha`` / ``strict_stop`` (stop on T(1-a) < eps instead of <=) / ``main_ids`` (int32 [H,W] filled with the
+    Gaussian of largest weight alpha*T, -1 none) serve the legacy conventions of oracle/legacy_torch.py."""
     tw = (W + TILE - 1) // TILE
     th = (H + TILE - 1) // TILE
     n_isect = vals.shape[0]
@@ -159,19 +168,25 @@ def blend(means2d, conics, opacities, feats, vals, offsets, W, H):
             T = torch.ones((), dtype=means2d.dtype)
             acc = torch.zeros(CH, dtype=means2d.dtype)
             cur = 0
+            best_w = 0.0
+            if main_ids is not None:
+                main_ids[i, j] = -1
             for k in range(start, end):
                 g = int(vals[k])
                 dx = means2d[g, 0] - px
                 dy = means2d[g, 1] - py
                 a, b, c = conics[g]
                 sigma = 0.5 * (a * dx * dx + c * dy * dy) + b * dx * dy
-                alpha = torch.clamp(opacities[g] * torch.exp(-sigma), max=MAX_ALPHA)
+                alpha = torch.clamp(opacities[g] * torch.exp(-sigma), max=max_alpha)
                 if float(sigma) < 0 or float(alpha) < ALPHA_THRESHOLD:
                     continue
                 nT = T * (1 - alpha)
-                if float(nT) <= T_EPS:
+                if (float(nT) < T_EPS) if strict_stop else (float(nT) <= T_EPS):
                     break
                 acc = acc + feats[g] * alpha * T
+                if main_ids is not None and float(alpha * T) > best_w:
+                    best_w = float(alpha * T)
+                    main_ids[i, j] = g
                 T = nT
                 cur = k
             row_c.append(acc)

@@ -1,16 +1,7 @@
-"""Drop-in for the names the LIVE reference path imports from ``diff_gaussian_rasterization``
-(Reconstruct/scene/optimizers.py:14): ``adamUpdate`` and ``adamUpdateBasic``.
-
-The legacy Inria-convention rasterizer (``GaussianRasterizationSettings`` / ``GaussianRasterizer``), used only by
-the off-path web viewer (Reconstruct/webviewer/scene_models.py:33-36, 559-605), is not provided
-in this round: importing those names raises with a pointer to gsplat-style ``artdeco_b200.rasterization``."""
+"""Drop-in for ``diff_gaussian_rasterization`` as the reference imports it:
+  * ``adamUpdate`` / ``adamUpdateBasic`` — the LIVE path (Reconstruct/scene/optimizers.py:14,48-57,90-99,116-128,144-156);
+  * ``GaussianRasterizationSettings`` / ``GaussianRasterizer`` / ``rasterize_gaussians`` — the legacy Inria-convention
+    rasterizer the web viewer uses (Reconstruct/webviewer/scene_models.py:33-36, 559-605).
+Everything runs through libartdeco_b200.so; there is no CPU fallback."""
 from artdeco_b200.adam import adamUpdate, adamUpdateBasic  # noqa: F401
-
-
-def __getattr__(name):
-    if name in ("GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"):
-        raise NotImplementedError(
-            f"diff_gaussian_rasterization.{name}: the legacy Inria-convention rasterizer is outside this round's scope "
-            "(SURVEY.md §8a R3, used only by the web viewer); the live path renders through gsplat.rendering.rasterization "
-            "-> artdeco_b200.rasterization")
-    raise AttributeError(name)
+from artdeco_b200.legacy import GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians  # noqa: F401

@@ -124,3 +124,67 @@ def test_single_pass_bf16_is_outside_tolerance(cuda):
     _, _, (f1, *_rest) = _run_cuda(g["cfg"], g["H"], g["W"], cuda, precision="bf16")
     e = rel_err(f1, g["enc1"])
     assert 1e-4 < e < 0.2
+
+
+@pytest.mark.gpu
+def test_symmetric_batch_wrapper_matches_per_pair_loop(cuda):
+    """utils_mast3r.py:42-71: the reference loops over pairs and runs decoder(i,j), decoder(j,i) per pair; the batched
+    wrapper must return the same X/C/D/Q stacking (ii, ji, jj, ij) as that loop run with our own per-pair decoder."""
+    from types import SimpleNamespace
+    from artdeco_b200.mast3r import AsymmetricMASt3R, wrappers
+    cfg, H, W = mt.SMALL_CFG, 64, 96
+    m = AsymmetricMASt3R(**cfg).load_state_dict(synthetic.det_weights(mt.param_shapes(cfg))).to(cuda)
+    img_i, img_j = synthetic.mast3r_pair(3, H, W, seed=5)
+    fi, pi, _ = m._encode_image(img_i.to(cuda), None)
+    fj, pj, _ = m._encode_image(img_j.to(cuda), None)
+    shapes = torch.tensor([[H, W]] * 3)
+    X, C, D, Q = wrappers.mast3r_decode_symmetric_batch(m, fi, pi, fj, pj, shapes, shapes)
+    assert X.shape == (4, 3, H, W, 3) and C.shape == (4, 3, H, W) and D.shape == (4, 3, H, W, 24) and Q.shape == (4, 3, H, W)
+    for b in range(3):
+        r11, r21 = wrappers.decoder(m, fi[b:b + 1], fj[b:b + 1], pi[b:b + 1], pj[b:b + 1], shapes[b], shapes[b])
+        r22, r12 = wrappers.decoder(m, fj[b:b + 1], fi[b:b + 1], pj[b:b + 1], pi[b:b + 1], shapes[b], shapes[b])
+        for n, r in enumerate((r11, r21, r22, r12)):
+            # same kernels, different batch size: tiling of the reductions is batch-independent -> tight agreement
+            assert rel_err(X[n, b], r["pts3d"][0]) < 2e-6 and rel_err(D[n, b], r["desc"][0]) < 2e-6
+            assert rel_err(C[n, b], r["conf"][0]) < 2e-6 and rel_err(Q[n, b], r["desc_conf"][0]) < 2e-6
+    # asymmetric / mono wrappers: shapes and agreement with the oracle on the same weights
+    fr_i, fr_j = SimpleNamespace(img=img_i[0].to(cuda)), SimpleNamespace(img=img_j[0].to(cuda))
+    Xa, Ca, Da, Qa, f1, p1 = wrappers.mast3r_asymmetric_inference(m, fr_i, fr_j)
+    assert Xa.shape == (2, H, W, 3) and Da.shape == (2, H, W, 24) and f1.shape[0] == 1
+    assert rel_err(Xa[0], X[0, 0]) < 2e-6 and rel_err(Xa[1], X[1, 0]) < 2e-6
+    Xii, Cii, feat, pos = wrappers.mast3r_inference_mono(m, fr_i)
+    assert Xii.shape == (H * W, 3) and Cii.shape == (H * W, 1)
+    sdg = {k: v.to(cuda) for k, v in synthetic.det_weights(mt.param_shapes(cfg)).items()}
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.inference_mode():
+            a1, _ = mt.forward_pair(sdg, cfg, img_i[:1].to(cuda), img_i[:1].to(cuda))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    assert rel_err(Xii, a1["pts3d"][0].reshape(-1, 3)) < 1e-4
+
+
+@pytest.mark.gpu
+def test_curope_inplace_matches_pytorch_rope(cuda):
+    """curope.rope_2d / cuRoPE2D (curope.cpp:49-68, curope2d.py:12-40) against the reference's PyTorch formulation
+    (croco/models/pos_embed.py:112-159, restated in oracle/mast3r_torch.py:rope2d), incl. the inverse rotation."""
+    from artdeco_b200.mast3r.curope import cuRoPE2D, rope_2d
+    g = torch.Generator().manual_seed(0)
+    for (B, Hh, N, D) in [(2, 12, 77, 64), (1, 3, 5, 32), (3, 16, 1024, 64)]:
+        # [B,H,N,D] VIEW of a [B,N,H,D] buffer, as croco's attention produces it (blocks.py:98-103)
+        tok = torch.randn(B, N, Hh, D, generator=g).transpose(1, 2)
+        pos = torch.stack([torch.randint(0, 32, (B, N), generator=g), torch.randint(0, 48, (B, N), generator=g)], -1)
+        ref = mt.rope2d(tok.double(), pos, base=100.0)
+        t = tok.transpose(1, 2).contiguous().to(cuda).transpose(1, 2)
+        out = cuRoPE2D(100.0)(t, pos.to(cuda))
+        assert out.data_ptr() == t.data_ptr(), "in place"
+        assert rel_err(out, ref) < 2e-6
+        # F0 = -1 undoes it (the reference's backward, curope2d.py:25-29)
+        bnhd = t.transpose(1, 2)
+        rope_2d(bnhd, pos.to(cuda), 100.0, -1.0)
+        assert rel_err(t, tok) < 2e-6
+    with pytest.raises(ValueError):
+        rope_2d(torch.zeros(1, 4, 2, 6, device=cuda), torch.zeros(1, 4, 2, dtype=torch.int64, device=cuda), 100.0, 1.0)
+    with pytest.raises(ValueError):
+        rope_2d(torch.zeros(1, 2, 4, 8, device=cuda).transpose(1, 2), torch.zeros(1, 4, 2, dtype=torch.int64, device=cuda), 100.0, 1.0)
