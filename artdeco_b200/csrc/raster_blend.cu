@@ -37,12 +37,43 @@ struct WarpRect {
     float xlo, xhi, ylo, yhi;  // pixel-centre range
 };
 
+// Can splat (A,B) reach alpha >= 1/255 anywhere in the warp's block?  Two conservative tests:
+//  1. the integer-radius box written by the projection (outside it alpha < 1/255 by construction of the radius);
+//  2. the exact minimum of sigma(d) = .5(a dx^2 + c dy^2) + b dx dy over the block's pixel-centre rectangle against the
+//     record's sigma_max = ln(255 o) + margin — the same bound the per-pixel pre-test uses, so a culled splat would have
+//     failed that pre-test on every pixel of the block and the image is unchanged.  For anisotropic splats the box is
+//     several times larger than the ellipse; this test costs ~1 warp-instruction per (warp, splat) because 32 splats
+//     are tested per instruction, against ~35 (forward) / ~110 (backward) for an evaluation it avoids.
 __device__ __forceinline__ bool splat_hits(const float4& A, const float4& B, const WarpRect& r) {
     const unsigned pr = __float_as_uint(B.w);
     // 65535 is the saturation value written by the projection: treat it as unbounded
     const float rx = (pr & 0xffffu) == 0xffffu ? 3.0e38f : (float)(pr & 0xffffu);
     const float ry = (pr >> 16) == 0xffffu ? 3.0e38f : (float)(pr >> 16);
-    return (A.x + rx >= r.xlo) && (A.x - rx <= r.xhi) && (A.y + ry >= r.ylo) && (A.y - ry <= r.yhi);
+    if (!((A.x + rx >= r.xlo) && (A.x - rx <= r.xhi) && (A.y + ry >= r.ylo) && (A.y - ry <= r.yhi))) return false;
+#ifndef ADB_NO_TIGHT_CULL
+    const float x0 = r.xlo - A.x, x1 = r.xhi - A.x, y0 = r.ylo - A.y, y1 = r.yhi - A.y;
+    if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;   // centre inside the block
+    const float a = A.z, b = A.w, c = B.x;
+    const float nb_c = -__fdividef(b, c), nb_a = -__fdividef(b, a);
+    // minimum over each edge (1-D quadratic, minimiser clamped to the edge); the rectangle's minimum is on its boundary
+    float m;
+    {
+        const float dy0 = fminf(y1, fmaxf(y0, nb_c * x0)), dy1 = fminf(y1, fmaxf(y0, nb_c * x1));
+        const float q0 = 0.5f * (a * x0 * x0 + c * dy0 * dy0) + b * x0 * dy0;
+        const float q1 = 0.5f * (a * x1 * x1 + c * dy1 * dy1) + b * x1 * dy1;
+        m = fminf(q0, q1);
+    }
+    {
+        const float dx0 = fminf(x1, fmaxf(x0, nb_a * y0)), dx1 = fminf(x1, fmaxf(x0, nb_a * y1));
+        const float q0 = 0.5f * (a * dx0 * dx0 + c * y0 * y0) + b * dx0 * y0;
+        const float q1 = 0.5f * (a * dx1 * dx1 + c * y1 * y1) + b * dx1 * y1;
+        m = fminf(m, fminf(q0, q1));
+    }
+    // rounding slack: the per-pixel test is sigma <= sigma_max in the same fp32 arithmetic
+    return m <= B.z * 1.0001f + 1e-4f;
+#else
+    return true;
+#endif
 }
 
 // LEGACY = Inria conventions (ADB_CONV_INRIA): alpha <= 0.99, stop when T(1-alpha) < 1e-4 (strict), 4th channel

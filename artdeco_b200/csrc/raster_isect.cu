@@ -157,3 +157,4 @@ ADB_API int adb_raster_tile_offsets(long long n_isect, const int64_t* keys_sorte
     ADB_CHECK_LAUNCH("tile_offsets_kernel");
     return ADB_OK;
 }
+

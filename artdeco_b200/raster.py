@@ -36,6 +36,7 @@ _lib.register("adb_raster_isect_emit_legacy", [i32, vp, vp, vp, i32, i32, i32, i
 _lib.register("adb_raster_blend_fwd_legacy", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp])
 _lib.register("adb_raster_blend_bwd_legacy", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 
+
 TILE = 16
 SPLAT_STRIDE = 12
 
