@@ -92,6 +92,28 @@ int adb_raster_blend_bwd_legacy(int W, int H, int n_per_cam, const float* splats
                                 const float* v_colors, const float* v_alphas, float* v_splats /*slot 9 = dL/d(1/z)*/,
                                 adb_stream_t stream);
 
+/* ---- dense matching after a MASt3R pair: mast3r_slam_backends.iter_proj / refine_matches
+ * (VSLAM/backend/src/matching_kernels.cu:26-116,119-316; bindings VSLAM/backend/src/gn.cpp:84-112) and the PyTorch glue of
+ * VSLAM/utils_matching.py:59-190.  All tensors contiguous, device pointers.
+ * adb_match_prep     X11,X21 [B,H,W,3] fp32; idx_init int64 [B,HW] or NULL (identity) -> rays_with_grad [B,H,W,9]
+ *                    (unit ray, d/du, d/dv with the [-3,-10,-3]/32 kernels, reflect padding), pts3d_norm [B,HW,3],
+ *                    p_init [B,HW,2] (u,v) fp32                                   (utils_matching.py:59-97,120-145)
+ * adb_iter_proj      per-point LM on the bilinear ray image -> p_new [B,n,2] fp32, converged u8 [B,n]  (kernels.cu:119-276)
+ * adb_match_finalize p1 = trunc(p) int64 [B,HW,2]; valid = converged && ||X11[p1]-X21|| < dist_thresh (utils_matching.py:166-174)
+ * adb_refine_matches D11 fp16 [B,H,W,F], D21 fp16 [B,n,F], p1 int64 [B,n,2] -> p1_new int64 [B,n,2] and (optional) the
+ *                    linear index u + W v [B,n]; F in {16,24,32}; fp16 score arithmetic as the reference's (kernels.cu:26-83) */
+int adb_match_prep(int B, int H, int W, const float* X11, const float* X21, const long long* idx_init,
+                   float* rays_with_grad, float* pts3d_norm, float* p_init, adb_stream_t stream);
+int adb_iter_proj(int B, int H, int W, int n_pts, const float* rays_with_grad, const float* pts3d_norm,
+                  const float* p_init, int max_iter, float lambda_init, float cost_thresh, float* p_new,
+                  unsigned char* converged, adb_stream_t stream);
+int adb_match_finalize(int B, int H, int W, const float* X11, const float* X21, const float* p,
+                       const unsigned char* converged, float dist_thresh, long long* p1, unsigned char* valid,
+                       adb_stream_t stream);
+int adb_refine_matches(int B, int H, int W, int fdim, int n_pts, const void* D11_f16, const void* D21_f16,
+                       const long long* p1, int radius, int dilation_max, long long* p1_new, long long* lin_idx,
+                       adb_stream_t stream);
+
 /* ---- covariance-modulation MLP (SceneModel.render, Reconstruct/scene/scene_models/h3dgsv3.py:656-662; mlp_cov :173-177) ----
  * x = cat(global_feat[cls_id], local_feat); o = W2 relu(W1 x + b1) + b2; scale_out = scaling*sigmoid(o[:3]);
  * rot_out = normalize(rotation*o[3:]).  D = Fg+Fl in {32,64}.  Backward ACCUMULATES v_global_feat, v_W1, v_b1, v_W2, v_b2. */

@@ -2,6 +2,7 @@
 /root/reference into oracle/_ref/ (git-ignored, travels to the GPU box with the snapshot), for sm_100:
   fused_ssim_ref   <- Reconstruct/submodules/fused-ssim/{ssim.cu,ext.cpp}      (flags of its setup.py:13-23)
   simple_knn_ref   <- Reconstruct/submodules/simple-knn/{simple_knn.cu,spatial.cu,ext.cpp}
+  mast3r_matching_ref <- VSLAM/backend/src/matching_kernels.cu + oracle/matching_bind.cpp (our binding; gn.cpp needs Eigen)
 No reference source is copied into the repo.  The built modules are used only by tests (bit/tolerance comparison of
 our kernels against the real reference on the GPU) and by bench tooling ("reference CUDA build on the same box")."""
 from __future__ import annotations
@@ -11,6 +12,8 @@ import sys
 from pathlib import Path
 
 REF = Path("/root/reference/Reconstruct/submodules")
+REF_ROOT = Path("/root/reference")
+HERE = Path(__file__).resolve().parent
 OUT = Path(__file__).resolve().parent / "_ref"
 
 EXTS = {
@@ -18,7 +21,18 @@ EXTS = {
                            cuda_flags=["-O3", "--maxrregcount=32", "--use_fast_math"]),
     "simple_knn_ref": dict(sources=["simple-knn/simple_knn.cu", "simple-knn/spatial.cu", "simple-knn/ext.cpp"],
                            cuda_flags=["-O3"]),
+    # the reference's matching kernels (flags of VSLAM/setup.py:62-67) behind our own two-function binding
+    "mast3r_matching_ref": dict(sources=["@VSLAM/backend/src/matching_kernels.cu", "#matching_bind.cpp"],
+                                cuda_flags=["-O3", "--use_fast_math", "-include", str(HERE / "ref_compat.h")]),
 }
+
+
+def _src(s: str) -> str:
+    if s.startswith("@"):
+        return str(REF_ROOT / s[1:])     # relative to the reference root
+    if s.startswith("#"):
+        return str(HERE / s[1:])         # our own file under oracle/
+    return str(REF / s)
 
 
 def _so(name: str) -> Path:
@@ -36,7 +50,7 @@ def build_all(verbose: bool = False) -> None:
             continue
         bdir = OUT / name
         bdir.mkdir(parents=True, exist_ok=True)
-        cpp_extension.load(name=name, sources=[str(REF / s) for s in cfg["sources"]],
+        cpp_extension.load(name=name, sources=[_src(s) for s in cfg["sources"]],
                            extra_cuda_cflags=cfg["cuda_flags"] + ["-gencode", "arch=compute_100,code=sm_100"],
                            extra_cflags=["-O3"], build_directory=str(bdir), verbose=verbose, is_python_module=False)
         print(f"[build_ref] built {_so(name)}")
