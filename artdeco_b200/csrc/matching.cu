@@ -160,7 +160,10 @@ match_finalize_kernel(int H, int W, const float* __restrict__ X11, const float* 
 // F halfs per descriptor, F % 8 == 0 (16-byte gathers).  Scores are formed exactly as the reference's c10::Half arithmetic
 // does (Half.h operator*, operator+=: float op, result rounded to half == HMUL / HADD in round-to-nearest): per candidate
 // s = 0; for k: s = rn16(s + rn16(d21[k] * d11[k])).  Two candidates ride in the two halves of a __half2.
-template <int F>
+// PLANAR: descriptors stored chunk-planar [b][F/8][pixels][8 halfs] (adb_desc_pack_f16): the 32 lanes of a warp, which
+// look at 32 neighbouring pixels, then read 512 contiguous bytes per 128-bit load (4 lines) instead of 16 B at a 48 B
+// stride (12 lines) -- the row-major kernel is bound by L1 wavefronts, not by arithmetic.
+template <int F, bool PLANAR>
 __global__ void __launch_bounds__(128)
 refine_matches_kernel(int H, int W, int n_pts, const __half* __restrict__ D11, const __half* __restrict__ D21,
                       const long long* __restrict__ p1, int radius, int dilation_max, long long* __restrict__ p1_new,
@@ -171,16 +174,19 @@ refine_matches_kernel(int H, int W, int n_pts, const __half* __restrict__ D11, c
     const size_t q = (size_t)b * n_pts + n;
     __half2 d2[F];   // query feature k duplicated in both halves
     {
-        const uint4* src = reinterpret_cast<const uint4*>(D21 + q * F);
+        const uint4* src = reinterpret_cast<const uint4*>(D21) + (PLANAR ? ((size_t)b * (F / 8) * n_pts + n) : q * (F / 8));
+        const size_t qstep = PLANAR ? (size_t)n_pts : 1;
 #pragma unroll
         for (int k8 = 0; k8 < F / 8; ++k8) {
-            const uint4 w = __ldg(src + k8);
+            const uint4 w = __ldg(src + k8 * qstep);
             const __half* hh = reinterpret_cast<const __half*>(&w);
 #pragma unroll
             for (int k = 0; k < 8; ++k) d2[k8 * 8 + k] = __half2half2(hh[k]);
         }
     }
-    const __half* img = D11 + (size_t)b * H * W * F;
+    const uint4* img = reinterpret_cast<const uint4*>(D11) + (size_t)b * H * W * (F / 8);
+    const size_t cstep = PLANAR ? (size_t)H * W : 1;      // distance between a pixel's consecutive 16-byte chunks
+    const size_t pstep = PLANAR ? 1 : (F / 8);           // distance between neighbouring pixels' first chunks
     long long u0 = p1[q * 2], v0 = p1[q * 2 + 1];
     long long u_new = u0, v_new = v0;
     // numeric_limits<Half>::min() (smallest positive normal, matching_kernels.cu:50): scores at or below it never win
@@ -197,12 +203,12 @@ refine_matches_kernel(int H, int W, int n_pts, const __half* __restrict__ D11, c
                 const bool a_ok = u_ok && va >= 0 && va < H;
                 const bool b_ok = u_ok && (j + 1 < cnt) && vb >= 0 && vb < H;
                 if (!a_ok && !b_ok) continue;
-                const uint4* pa = reinterpret_cast<const uint4*>(img + ((size_t)(a_ok ? va : vb) * W + uu) * F);
-                const uint4* pb = reinterpret_cast<const uint4*>(img + ((size_t)(b_ok ? vb : va) * W + uu) * F);
+                const uint4* pa = img + ((size_t)(a_ok ? va : vb) * W + uu) * pstep;
+                const uint4* pb = img + ((size_t)(b_ok ? vb : va) * W + uu) * pstep;
                 __half2 s = __float2half2_rn(0.f);
 #pragma unroll
                 for (int k8 = 0; k8 < F / 8; ++k8) {
-                    const uint4 wa = __ldg(pa + k8), wb = __ldg(pb + k8);
+                    const uint4 wa = __ldg(pa + k8 * cstep), wb = __ldg(pb + k8 * cstep);
                     const __half* ha = reinterpret_cast<const __half*>(&wa);
                     const __half* hb = reinterpret_cast<const __half*>(&wb);
 #pragma unroll
@@ -222,7 +228,38 @@ refine_matches_kernel(int H, int W, int n_pts, const __half* __restrict__ D11, c
     if (lin_idx) lin_idx[q] = u_new + (long long)W * v_new;
 }
 
+// fp32 [b, pixels, F] -> fp16 (round to nearest, == .half()) in the chunk-planar layout [b][F/8][pixels][8]
+template <int F>
+__global__ void __launch_bounds__(256)
+desc_pack_kernel(long long n_pix, const float* __restrict__ src, __half* __restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, chunk) pairs, chunk fastest
+    const int b = blockIdx.y;
+    if (i >= n_pix * (F / 8)) return;
+    const long long pix = i / (F / 8);
+    const int k8 = (int)(i - pix * (F / 8));
+    const float4* s4 = reinterpret_cast<const float4*>(src + ((size_t)b * n_pix + pix) * F + k8 * 8);
+    const float4 x = __ldg(s4), y = __ldg(s4 + 1);
+    __half2 h[4] = {__floats2half2_rn(x.x, x.y), __floats2half2_rn(x.z, x.w), __floats2half2_rn(y.x, y.y),
+                    __floats2half2_rn(y.z, y.w)};
+    reinterpret_cast<uint4*>(dst)[((size_t)b * (F / 8) + k8) * n_pix + pix] = *reinterpret_cast<uint4*>(h);
+}
+
 }  // namespace
+
+ADB_API int adb_desc_pack_f16(int B, long long n_pix, int fdim, const float* src, void* dst_f16, cudaStream_t stream) {
+    ADB_REQUIRE(B >= 0 && n_pix >= 0, "adb_desc_pack_f16: bad sizes");
+    ADB_REQUIRE(fdim == 16 || fdim == 24 || fdim == 32, "adb_desc_pack_f16: descriptor dim must be 16, 24 or 32");
+    if (B == 0 || n_pix == 0) return ADB_OK;
+    ADB_REQUIRE(src && dst_f16, "adb_desc_pack_f16: null pointer");
+    ADB_REQUIRE(((uintptr_t)src | (uintptr_t)dst_f16) % 16 == 0, "adb_desc_pack_f16: buffers must be 16-byte aligned");
+    dim3 grid((unsigned)adb_cdiv(n_pix * (fdim / 8), 256), B);
+    __half* d = (__half*)dst_f16;
+    if (fdim == 16) desc_pack_kernel<16><<<grid, 256, 0, stream>>>(n_pix, src, d);
+    else if (fdim == 24) desc_pack_kernel<24><<<grid, 256, 0, stream>>>(n_pix, src, d);
+    else desc_pack_kernel<32><<<grid, 256, 0, stream>>>(n_pix, src, d);
+    ADB_CHECK_LAUNCH("desc_pack_kernel");
+    return ADB_OK;
+}
 
 ADB_API int adb_match_prep(int B, int H, int W, const float* X11, const float* X21, const long long* idx_init,
                            float* rays_with_grad, float* pts3d_norm, float* p_init, cudaStream_t stream) {
@@ -261,7 +298,7 @@ ADB_API int adb_match_finalize(int B, int H, int W, const float* X11, const floa
 }
 
 ADB_API int adb_refine_matches(int B, int H, int W, int fdim, int n_pts, const void* D11_f16, const void* D21_f16,
-                               const long long* p1, int radius, int dilation_max, long long* p1_new,
+                               int planar, const long long* p1, int radius, int dilation_max, long long* p1_new,
                                long long* lin_idx, cudaStream_t stream) {
     ADB_REQUIRE(B >= 0 && H > 0 && W > 0 && n_pts >= 0 && radius >= 0 && dilation_max >= 0, "adb_refine_matches: bad sizes");
     ADB_REQUIRE(fdim == 16 || fdim == 24 || fdim == 32, "adb_refine_matches: descriptor dim must be 16, 24 or 32");
@@ -271,12 +308,13 @@ ADB_API int adb_refine_matches(int B, int H, int W, int fdim, int n_pts, const v
     dim3 grid(adb_cdiv(n_pts, 128), B);
     const __half* a = (const __half*)D11_f16;
     const __half* c = (const __half*)D21_f16;
-    if (fdim == 16)
-        refine_matches_kernel<16><<<grid, 128, 0, stream>>>(H, W, n_pts, a, c, p1, radius, dilation_max, p1_new, lin_idx);
-    else if (fdim == 24)
-        refine_matches_kernel<24><<<grid, 128, 0, stream>>>(H, W, n_pts, a, c, p1, radius, dilation_max, p1_new, lin_idx);
-    else
-        refine_matches_kernel<32><<<grid, 128, 0, stream>>>(H, W, n_pts, a, c, p1, radius, dilation_max, p1_new, lin_idx);
+#define ADB_REFINE(FD, PL) refine_matches_kernel<FD, PL><<<grid, 128, 0, stream>>>(H, W, n_pts, a, c, p1, radius, dilation_max, p1_new, lin_idx)
+    if (planar) {
+        if (fdim == 16) ADB_REFINE(16, true); else if (fdim == 24) ADB_REFINE(24, true); else ADB_REFINE(32, true);
+    } else {
+        if (fdim == 16) ADB_REFINE(16, false); else if (fdim == 24) ADB_REFINE(24, false); else ADB_REFINE(32, false);
+    }
+#undef ADB_REFINE
     ADB_CHECK_LAUNCH("refine_matches_kernel");
     return ADB_OK;
 }

@@ -6,13 +6,13 @@ batch in Python and runs the decoder twice and the heads four times PER PAIR (ut
 goes through ONE decoder call on the concatenation [i|j] x [j|i] and ONE call per head, which is the same computation
 (pairs are independent; both directions share the weights) on a 2B batch.
 
-The matching wrappers (``mast3r_match_symmetric / _asymmetric``) need the dense matching kernels
-and are not part of this module.
+``mast3r_match_symmetric / mast3r_match_asymmetric`` chain into ``artdeco_b200.matching`` (the dense matching kernels).
 """
 from __future__ import annotations
 
 import torch
 
+from .. import matching
 from .model import AsymmetricMASt3R
 
 
@@ -98,3 +98,34 @@ def mast3r_inference_mono(model, frame):
     Xii = res11["pts3d"][0].reshape(-1, 3)
     Cii = res11["conf"][0].reshape(-1, 1)
     return Xii, Cii, feat, pos
+
+
+def mast3r_match_symmetric(config, model, feat_i, pos_i, feat_j, pos_j, shape_i, shape_j):
+    """utils_mast3r.py:74-112: decode both directions, match j->i and i->j in one batched call."""
+    X, C, D, Q = mast3r_decode_symmetric_batch(model, feat_i, pos_i, feat_j, pos_j, shape_i, shape_j)
+    b = X.shape[1]
+    Xii, Xji, Xjj, Xij = X[0], X[1], X[2], X[3]
+    Dii, Dji, Djj, Dij = D[0], D[1], D[2], D[3]
+    Qii, Qji, Qjj, Qij = Q[0], Q[1], Q[2], Q[3]
+    X11, X21 = torch.cat((Xii, Xjj), 0), torch.cat((Xji, Xij), 0)
+    D11, D21 = torch.cat((Dii, Djj), 0), torch.cat((Dji, Dij), 0)
+    idx_1_to_2, valid_match_2 = matching.match(config, X11, X21, D11, D21)
+    match_b = X11.shape[0] // 2
+    return (idx_1_to_2[:match_b], idx_1_to_2[match_b:], valid_match_2[:match_b], valid_match_2[match_b:],
+            Qii.reshape(b, -1, 1), Qjj.reshape(b, -1, 1), Qji.reshape(b, -1, 1), Qij.reshape(b, -1, 1))
+
+
+def mast3r_match_asymmetric(config, model, frame_i, frame_j, idx_i2j_init=None, embeddings_i=None, embeddings_j=None):
+    """utils_mast3r.py:144-171."""
+    X, C, D, Q, feat1, pos1 = mast3r_asymmetric_inference(model, frame_i, frame_j, embeddings_i=embeddings_i,
+                                                          embeddings_j=embeddings_j)
+    b = X.shape[0] // 2
+    Xii, Xji = X[:b], X[b:]
+    Dii, Dji = D[:b], D[b:]
+    idx_i2j, valid_match_j = matching.match(config, Xii.contiguous(), Xji.contiguous(), Dii.contiguous(),
+                                            Dji.contiguous(), idx_1_to_2_init=idx_i2j_init)
+    hw = X.shape[1] * X.shape[2]
+    Xii, Xji = X.reshape(2 * b, hw, 3)
+    Cii, Cji = C.reshape(2 * b, hw, 1)
+    Qii, Qji = Q.reshape(2 * b, hw, 1)
+    return idx_i2j, valid_match_j, Xii, Cii, Qii, Xji, Cji, Qji, feat1, pos1

@@ -8,12 +8,13 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import f32, i32, vp
+from ._lib import f32, i32, i64, vp
 
 _lib.register("adb_match_prep", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp])
 _lib.register("adb_iter_proj", [i32, i32, i32, i32, vp, vp, vp, i32, f32, f32, vp, vp, vp])
 _lib.register("adb_match_finalize", [i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp])
-_lib.register("adb_refine_matches", [i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp])
+_lib.register("adb_refine_matches", [i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp, vp, vp])
+_lib.register("adb_desc_pack_f16", [i32, i64, i32, vp, vp, vp])
 
 
 def _chk(t, name, dtype):
@@ -54,9 +55,20 @@ def refine_matches(D11, D21, p1, radius, dilation_max, return_linear: bool = Fal
     p1_new = torch.empty_like(p1)
     lin = torch.empty(b, n, dtype=torch.int64, device=p1.device) if return_linear else None
     with torch.cuda.device(p1.device):
-        _lib.call("adb_refine_matches", b, h, w, F_, n, _lib.ptr(D11), _lib.ptr(D21), _lib.ptr(p1), int(radius),
+        _lib.call("adb_refine_matches", b, h, w, F_, n, _lib.ptr(D11), _lib.ptr(D21), 0, _lib.ptr(p1), int(radius),
                   int(dilation_max), _lib.ptr(p1_new), _lib.ptr(lin), _lib.stream())
     return [p1_new, lin] if return_linear else [p1_new]
+
+
+def _pack_f16(D, b, n_pix):
+    """fp32 descriptors [b, n_pix, F] -> fp16 chunk-planar (adb_desc_pack_f16); same rounding as ``.half()``."""
+    D = D.reshape(b, n_pix, -1)
+    if D.dtype != torch.float32:
+        D = D.float()
+    D = D.contiguous()
+    out = torch.empty(b * n_pix * D.shape[-1], dtype=torch.float16, device=D.device)
+    _lib.call("adb_desc_pack_f16", b, n_pix, D.shape[-1], _lib.ptr(D), _lib.ptr(out), _lib.stream())
+    return out, D.shape[-1]
 
 
 def pixel_to_lin(p1, w):
@@ -111,8 +123,14 @@ def match_iterative_proj(config, X11, X21, D11, D21, idx_1_to_2_init=None):
     b, h, w = X21.shape[:3]
     p1, valid = _project_and_filter(cfg, X11, X21, idx_1_to_2_init)
     if cfg["radius"] > 0:
-        _, idx = refine_matches(D11.half().contiguous(), D21.reshape(b, h * w, -1).half().contiguous(), p1, cfg["radius"],
-                                cfg["dilation_max"], return_linear=True)
+        # fp32 -> fp16 conversion fused with the re-layout that makes the window gathers coalesce; identical arithmetic
+        idx = torch.empty(b, h * w, dtype=torch.int64, device=p1.device)
+        p1_new = torch.empty_like(p1)
+        with torch.cuda.device(p1.device):
+            a, F_ = _pack_f16(D11, b, h * w)
+            q, _ = _pack_f16(D21, b, h * w)
+            _lib.call("adb_refine_matches", b, h, w, F_, h * w, _lib.ptr(a), _lib.ptr(q), 1, _lib.ptr(p1),
+                      int(cfg["radius"]), int(cfg["dilation_max"]), _lib.ptr(p1_new), _lib.ptr(idx), _lib.stream())
     else:
         idx = pixel_to_lin(p1, w)
     return idx, valid.unsqueeze(-1)

@@ -111,8 +111,12 @@ int adb_match_finalize(int B, int H, int W, const float* X11, const float* X21, 
                        const unsigned char* converged, float dist_thresh, long long* p1, unsigned char* valid,
                        adb_stream_t stream);
 int adb_refine_matches(int B, int H, int W, int fdim, int n_pts, const void* D11_f16, const void* D21_f16,
+                       int planar /*0: row-major [.,F] as the reference passes them; 1: adb_desc_pack_f16 layout*/,
                        const long long* p1, int radius, int dilation_max, long long* p1_new, long long* lin_idx,
                        adb_stream_t stream);
+/* fp32 [B,n_pix,F] -> fp16 (round to nearest even, == Tensor.half()) chunk-planar [B][F/8][n_pix][8]: the layout in which a
+ * warp's 128-bit descriptor gathers coalesce (utils_matching.py:178-184 converts with .half() and keeps [.,F] rows). */
+int adb_desc_pack_f16(int B, long long n_pix, int fdim, const float* src, void* dst_f16, adb_stream_t stream);
 
 /* ---- covariance-modulation MLP (SceneModel.render, Reconstruct/scene/scene_models/h3dgsv3.py:656-662; mlp_cov :173-177) ----
  * x = cat(global_feat[cls_id], local_feat); o = W2 relu(W1 x + b1) + b2; scale_out = scaling*sigmoid(o[:3]);

@@ -152,6 +152,16 @@ def test_symmetric_batch_wrapper_matches_per_pair_loop(cuda):
     Xa, Ca, Da, Qa, f1, p1 = wrappers.mast3r_asymmetric_inference(m, fr_i, fr_j)
     assert Xa.shape == (2, H, W, 3) and Da.shape == (2, H, W, 24) and f1.shape[0] == 1
     assert rel_err(Xa[0], X[0, 0]) < 2e-6 and rel_err(Xa[1], X[1, 0]) < 2e-6
+    # matching wrappers (utils_mast3r.py:74-112,144-171) chain the decode into artdeco_b200.matching
+    cfgm = {"matching": dict(max_iter=10, lambda_init=1e-8, convergence_thresh=1e-6, dist_thresh=1e-1, radius=2, dilation_max=2)}
+    out = wrappers.mast3r_match_symmetric(cfgm, m, fi, pi, fj, pj, shapes, shapes)
+    assert len(out) == 8 and out[0].shape == (3, H * W) and out[2].shape == (3, H * W, 1) and out[4].shape == (3, H * W, 1)
+    from artdeco_b200 import matching
+    i2j, vj = matching.match(cfgm, torch.cat((X[0], X[2]), 0), torch.cat((X[1], X[3]), 0), torch.cat((D[0], D[2]), 0),
+                             torch.cat((D[1], D[3]), 0))
+    assert torch.equal(out[0], i2j[:3]) and torch.equal(out[1], i2j[3:]) and torch.equal(out[3], vj[3:])
+    oa = wrappers.mast3r_match_asymmetric(cfgm, m, fr_i, fr_j)
+    assert len(oa) == 10 and oa[0].shape == (1, H * W) and oa[2].shape == (H * W, 3) and oa[4].shape == (H * W, 1)
     Xii, Cii, feat, pos = wrappers.mast3r_inference_mono(m, fr_i)
     assert Xii.shape == (H * W, 3) and Cii.shape == (H * W, 1)
     sdg = {k: v.to(cuda) for k, v in synthetic.det_weights(mt.param_shapes(cfg)).items()}

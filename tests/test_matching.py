@@ -131,6 +131,10 @@ def test_match_end_to_end_at_512(cuda):
     idx_o, valid_o, _, _ = mr.match_iterative_proj(CFG["matching"], X11, X21, D11, D21)
     assert (valid == valid_o).float().mean() >= 0.999
     assert (idx == idx_o).float().mean() >= 0.995      # a sub-pixel position next to an integer boundary may truncate differently
+    # the fused flow's chunk-planar fp16 descriptors must give exactly what the row-major kernel gives on the same p1
+    p1, v1 = M._project_and_filter(CFG["matching"], X11, X21, None)
+    _, lin = M.refine_matches(D11.half().contiguous(), D21.reshape(2, -1, 24).half().contiguous(), p1, 4, 5, return_linear=True)
+    assert torch.equal(lin, idx) and torch.equal(v1.unsqueeze(-1), valid)
     Dr = torch.nn.functional.normalize(torch.randn(2, 512, 512, 24, generator=torch.Generator().manual_seed(7)), dim=-1).to(cuda)
     ident, v2 = M.match(CFG, X11, X11, Dr, Dr)
     grid = torch.arange(512 * 512, device=cuda).view(512, 512)[1:-1, 1:-1].reshape(-1)
