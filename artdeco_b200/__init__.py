@@ -8,12 +8,13 @@ Public operators (same names / argument meaning as the reference's, see each mod
   cull.lod_select, cull.lod_cull                       (SceneModel.render's d_max cull)
   covmlp.cov_mlp_modulate                              (SceneModel.render's mlp_cov scale/rotation modulation)
   matching.iter_proj, matching.refine_matches, matching.match   (mast3r_slam_backends + utils_matching)
+  optimizers.BaseAdam, optimizers.SparseGaussianAdam   (Reconstruct/scene/optimizers.py: fused step, one-launch add_and_prune)
   legacy.GaussianRasterizer, legacy.rasterize_gaussians  (diff_gaussian_rasterization legacy API, web viewer)
 There is no CPU implementation: every operator raises unless a CUDA sm_100 device and the C-ABI library
 ``libartdeco_b200.so`` are available.
 """
 from . import _lib  # noqa: F401
-from . import adam, covmlp, cull, knn, legacy, mast3r, matching, raster  # noqa: F401  (each registers its C signatures)
+from . import adam, covmlp, cull, knn, legacy, mast3r, matching, optimizers, raster  # noqa: F401  (each registers its C signatures)
 from .adam import adamUpdate, adamUpdateBasic  # noqa: F401
 from .covmlp import cov_mlp_modulate  # noqa: F401
 from .cull import lod_cull, lod_select  # noqa: F401

@@ -18,11 +18,15 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 }
 
 // lr_mode: 0 scalar (host), 1 device numel 1, 2 per row, 3 per element
-template <int VEC>
+// DECAY (lr_mode 3 only): after the update the element's own learning rate becomes max(lr * lr_decay, lr_min) -- the
+// per-primitive schedule SparseGaussianAdam.step applies with `lr[visibility] *= decay; lr.clamp_min_(0.1 lr_init)`
+// (optimizers.py:130-133,158-161), fused so the lr tensor is read and written in the same pass.
+template <int VEC, bool DECAY>
 __global__ void __launch_bounds__(256)
 adam_kernel(long long N, long long M, float* __restrict__ param, const float* __restrict__ grad,
             float* __restrict__ m1, float* __restrict__ m2, const unsigned char* __restrict__ visible,
-            const float* __restrict__ lr_dev, int lr_mode, float lr_scalar, float b1, float b2, float eps) {
+            const float* lr_dev, int lr_mode, float lr_scalar, float b1, float b2, float eps,
+            float* lr_mut, float lr_decay, float lr_min) {
     const long long total = N * M / VEC;
     const long long mv = M / VEC;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -46,11 +50,15 @@ adam_kernel(long long N, long long M, float* __restrict__ param, const float* __
             reinterpret_cast<float4*>(param)[i] = p;
             reinterpret_cast<float4*>(m1)[i] = a;
             reinterpret_cast<float4*>(m2)[i] = v;
+            if (DECAY)
+                reinterpret_cast<float4*>(lr_mut)[i] = make_float4(fmaxf(l.x * lr_decay, lr_min), fmaxf(l.y * lr_decay, lr_min),
+                                                                   fmaxf(l.z * lr_decay, lr_min), fmaxf(l.w * lr_decay, lr_min));
         } else {
-            if (lr_mode == 3) lr = __ldg(lr_dev + i);
+            if (lr_mode == 3) lr = lr_dev[i];
             float p = param[i], a = m1[i], v = m2[i];
             adam1(p, grad[i], a, v, lr, b1, b2, eps);
             param[i] = p; m1[i] = a; m2[i] = v;
+            if (DECAY) lr_mut[i] = fmaxf(lr * lr_decay, lr_min);
         }
     }
 }
@@ -77,11 +85,33 @@ ADB_API int adb_adam_update(long long N, long long M, float* param, const float*
     const long long work = vec ? N * M / 4 : N * M;
     const int blocks = (int)((work + 255) / 256 < 148LL * 16 ? (work + 255) / 256 : 148LL * 16);
     if (vec)
-        adam_kernel<4><<<blocks, 256, 0, stream>>>(N, M, param, grad, m1, m2, visible, lr_dev, lr_mode, lr_scalar, b1,
-                                                  b2, eps);
+        adam_kernel<4, false><<<blocks, 256, 0, stream>>>(N, M, param, grad, m1, m2, visible, lr_dev, lr_mode, lr_scalar,
+                                                         b1, b2, eps, nullptr, 1.f, 0.f);
     else
-        adam_kernel<1><<<blocks, 256, 0, stream>>>(N, M, param, grad, m1, m2, visible, lr_dev, lr_mode, lr_scalar, b1,
-                                                  b2, eps);
+        adam_kernel<1, false><<<blocks, 256, 0, stream>>>(N, M, param, grad, m1, m2, visible, lr_dev, lr_mode, lr_scalar,
+                                                         b1, b2, eps, nullptr, 1.f, 0.f);
     ADB_CHECK_LAUNCH("adam_kernel");
+    return ADB_OK;
+}
+
+// Adam step + per-element learning-rate decay in one pass.  lr [N,M] (same shape as param) is read, used, and overwritten
+// with max(lr * lr_decay, lr_min) on visible rows (optimizers.py:116-133,144-161).
+ADB_API int adb_adam_update_decay(long long N, long long M, float* param, const float* grad, float* m1, float* m2,
+                                  const unsigned char* visible, float* lr, float b1, float b2, float eps,
+                                  float lr_decay, float lr_min, cudaStream_t stream) {
+    ADB_REQUIRE(N >= 0 && M >= 0, "adb_adam_update_decay: negative size");
+    if (N * M == 0) return ADB_OK;
+    ADB_REQUIRE(param && grad && m1 && m2 && lr, "adb_adam_update_decay: null pointer");
+    const bool vec = (M % 4 == 0) && ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m1 | (uintptr_t)m2 |
+                                        (uintptr_t)lr) & 15) == 0);
+    const long long work = vec ? N * M / 4 : N * M;
+    const int blocks = (int)((work + 255) / 256 < 148LL * 16 ? (work + 255) / 256 : 148LL * 16);
+    if (vec)
+        adam_kernel<4, true><<<blocks, 256, 0, stream>>>(N, M, param, grad, m1, m2, visible, lr, 3, 0.f, b1, b2, eps, lr,
+                                                        lr_decay, lr_min);
+    else
+        adam_kernel<1, true><<<blocks, 256, 0, stream>>>(N, M, param, grad, m1, m2, visible, lr, 3, 0.f, b1, b2, eps, lr,
+                                                        lr_decay, lr_min);
+    ADB_CHECK_LAUNCH("adam_kernel<decay>");
     return ADB_OK;
 }

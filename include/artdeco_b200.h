@@ -118,6 +118,22 @@ int adb_refine_matches(int B, int H, int W, int fdim, int n_pts, const void* D11
  * warp's 128-bit descriptor gathers coalesce (utils_matching.py:178-184 converts with .half() and keeps [.,F] rows). */
 int adb_desc_pack_f16(int B, long long n_pix, int fdim, const float* src, void* dst_f16, adb_stream_t stream);
 
+/* ---- optimizer bookkeeping (Reconstruct/scene/optimizers.py) ----
+ * adb_adam_update_decay  SparseGaussianAdam.step's update + its per-primitive learning-rate schedule in one pass
+ *                        (optimizers.py:116-133,144-161): lr [N,M] is used, then overwritten with max(lr*decay, lr_min) on
+ *                        visible rows.
+ * adb_compact_*          SparseGaussianAdam.add_and_prune (optimizers.py:163-219): out = cat(t[mask], ext) for
+ *                        every state tensor with one index plan and one gather launch (rows moved as 32-bit words). */
+int adb_adam_update_decay(long long N, long long M, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                          const unsigned char* visible, float* lr /*[N,M] in/out*/, float b1, float b2, float eps,
+                          float lr_decay, float lr_min, adb_stream_t stream);
+int adb_compact_workspace_bytes(long long N, size_t* bytes);
+int adb_compact_plan(long long N, const unsigned char* mask, int32_t* src_of /*[N]*/, int32_t* n_keep_dev /*[1]*/, void* ws,
+                     size_t ws_bytes, adb_stream_t stream);
+int adb_compact_gather(long long n_keep, long long n_ext, const int32_t* src_of, int n_tensors,
+                       const void* const* srcs /*HOST array of device pointers*/, void* const* dsts, const void* const* exts,
+                       const int* row_words, const unsigned* fill_words, adb_stream_t stream);
+
 /* ---- covariance-modulation MLP (SceneModel.render, Reconstruct/scene/scene_models/h3dgsv3.py:656-662; mlp_cov :173-177) ----
  * x = cat(global_feat[cls_id], local_feat); o = W2 relu(W1 x + b1) + b2; scale_out = scaling*sigmoid(o[:3]);
  * rot_out = normalize(rotation*o[3:]).  D = Fg+Fl in {32,64}.  Backward ACCUMULATES v_global_feat, v_W1, v_b1, v_W2, v_b2. */
