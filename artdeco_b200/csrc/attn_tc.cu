@@ -10,10 +10,14 @@
 //   TMA producer warp     Q tile once; K blocks through a 2-stage ring (read twice: see below); V^T blocks (1 stage)
 //   MMA warp (1 thread)   S_j = Q K_j^T  (tcgen05.mma M128 N128 K16, bf16x3 = 12 MMAs) into one of two TMEM S buffers;
 //                         O += P_j V_j   (M128 N64 K16, bf16x3 = 24 MMAs) into a TMEM O accumulator
-//   4 softmax warps       thread == query row.  PASS 1 reads every S_j and keeps only the row maximum.  PASS 2 recomputes
-//                         S_j (the tensor pipe is cheap here), forms p = exp2((s - max) * scale*log2e), accumulates the row
-//                         sum, and writes P_j as a bf16 (hi, lo) pair straight into shared memory in the 128-byte-swizzled
-//                         K-major layout the UMMA descriptor expects — the A operand of the P V product.
+//   8 softmax warps       two warps per TMEM lane quarter: thread == (query row, 64-key half of each key block).
+//                         PASS 1 reads every S_j (computed from the bf16 HI parts only: the subtracted maximum only has to
+//                         be close to the true one, softmax is invariant to it) and keeps the row maximum.  PASS 2 recomputes
+//                         S_j in bf16x3, forms p = exp2((s - max) * scale*log2e), accumulates the row sum, and writes its
+//                         64-key half of P_j as a bf16 (hi, lo) pair straight into shared memory in the 128-byte-swizzled
+//                         K-major layout the UMMA descriptor expects — the A operand of the P V product.  The two halves are
+//                         independent pipeline stages (own full/empty barriers): P V of one half overlaps the exponentials
+//                         of the other and of the next block.
 //   Two passes instead of an online-softmax rescale: the running-max correction would need a TMEM read-modify-write of O
 //   per key block; recomputing Q K^T costs 12 extra MMAs per block and keeps O a pure accumulate chain.
 // Precision: bf16x3 everywhere (same contract as csrc/gemm_tc.cu); exp via ex2.approx (2 ulp).
@@ -24,7 +28,7 @@
 
 namespace {
 
-constexpr int NT = 192;                  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 softmax
+constexpr int NT = 320;                  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..9 softmax
 constexpr int QT = 128, KT = 128, HD = 64;
 constexpr int TILE16 = 128 * 64 * 2;     // [128 rows x 64 cols] bf16 = 16 KB
 constexpr int TILE8 = 64 * 64 * 2;       // [64 rows x 64 cols] bf16 = 8 KB
@@ -98,6 +102,13 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
     d |= (uint32_t)(128 >> 4) << 24;
     return d;
 }
+// one MUFU.EX2; exp2f() wraps it in a denormal-range rescale (FSETP + 2 predicated FMUL) that softmax weights below 2^-126
+// do not need -- they flush to zero
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -117,10 +128,11 @@ constexpr int OFF_K = OFF_Q + 2 * TILE16;      // 2 stages x (K hi, K lo)   64 K
 constexpr int OFF_V = OFF_K + 4 * TILE16;      // V^T: 2 key-chunks x (hi, lo) x 8 KB = 32 KB
 constexpr int OFF_P = OFF_V + 4 * TILE8;       // P: 2 key-chunks x (hi, lo) x 16 KB = 64 KB
 constexpr int OFF_BAR = OFF_P + 4 * TILE16;    // barriers
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int OFF_RED = OFF_BAR + 256;         // [2 halves][128 rows] floats: row max / row sum exchange
+constexpr int SMEM_BYTES = OFF_RED + 2 * 128 * 4 + 1024;
 
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 6, B_SFULL = 7, B_SEMPTY = 9, B_PFULL = 11,
-       B_PEMPTY = 12, B_OFULL = 13, B_COUNT = 14 };
+       B_PEMPTY = 13, B_OFULL = 15, B_COUNT = 16 };
 
 __global__ void __launch_bounds__(NT, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo,
@@ -142,10 +154,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
         mbar_init(bar + B_QFULL, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar + B_KFULL + s, 1); mbar_init(bar + B_KEMPTY + s, 1);
-            mbar_init(bar + B_SFULL + s, 1); mbar_init(bar + B_SEMPTY + s, 4);
+            mbar_init(bar + B_SFULL + s, 1); mbar_init(bar + B_SEMPTY + s, 8);
+            mbar_init(bar + B_PFULL + s, 4); mbar_init(bar + B_PEMPTY + s, 1);
         }
         mbar_init(bar + B_VFULL, 1); mbar_init(bar + B_VEMPTY, 1);
-        mbar_init(bar + B_PFULL, 4); mbar_init(bar + B_PEMPTY, 1);
         mbar_init(bar + B_OFULL, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -168,9 +180,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
                 const int j = it % nb, s = it & 1;
                 mbar_wait(bar + B_KEMPTY + s, ((it >> 1) & 1) ^ 1);
                 uint8_t* st = smem + OFF_K + s * 2 * TILE16;
-                mbar_expect_tx(bar + B_KFULL + s, kstage_bytes);
+                const bool lo = x3 && it >= nb;             // pass 1 multiplies the hi parts only
+                mbar_expect_tx(bar + B_KFULL + s, lo ? kstage_bytes : (uint32_t)TILE16);
                 tma_load_3d(st, &mKhi, bar + B_KFULL + s, 0, j * KT, bh);
-                if (x3) tma_load_3d(st + TILE16, &mKlo, bar + B_KFULL + s, 0, j * KT, bh);
+                if (lo) tma_load_3d(st + TILE16, &mKlo, bar + B_KFULL + s, 0, j * KT, bh);
                 if (it >= nb) {                            // pass 2: the matching V^T block (two 64-key chunks)
                     mbar_wait(bar + B_VEMPTY, (j & 1) ^ 1);
                     mbar_expect_tx(bar + B_VFULL, v_bytes);
@@ -190,7 +203,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
         const uint32_t qa = smem_u32(smem + OFF_Q);
         mbar_wait(bar + B_QFULL, 0);
         tc_fence_after();
-        auto issue_S = [&](int it) {        // S[it&1] = Q K^T for K ring slot it&1
+        auto issue_S = [&](int it, bool full) {   // S[it&1] = Q K^T for K ring slot it&1 (full: bf16x3, else hi x hi)
             const int s = it & 1;
             mbar_wait(bar + B_KFULL + s, (it >> 1) & 1);
             mbar_wait(bar + B_SEMPTY + s, ((it >> 1) & 1) ^ 1);
@@ -204,7 +217,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
                 for (int k = 0; k < HD / 16; ++k) {
                     const uint64_t adv = (uint64_t)((k * 32) >> 4);
                     tc_mma(td, dQh + adv, dKh + adv, idS, k ? 1u : 0u);
-                    if (x3) {
+                    if (x3 && full) {
                         tc_mma(td, dQh + adv, dKl + adv, idS, 1u);
                         tc_mma(td, dQl + adv, dKh + adv, idS, 1u);
                     }
@@ -214,18 +227,18 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             }
             __syncwarp();
         };
-        for (int it = 0; it < nb; ++it) issue_S(it);                // pass 1
-        issue_S(nb);                                                 // first S of pass 2
+        for (int it = 0; it < nb; ++it) issue_S(it, false);         // pass 1
+        issue_S(nb, true);                                           // first S of pass 2
         for (int j = 0; j < nb; ++j) {
-            if (j + 1 < nb) issue_S(nb + j + 1);                     // overlap the next S with this block's softmax
-            mbar_wait(bar + B_PFULL, j & 1);
+            if (j + 1 < nb) issue_S(nb + j + 1, true);               // overlap the next S with this block's softmax
             mbar_wait(bar + B_VFULL, j & 1);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t pa = smem_u32(smem + OFF_P), va = smem_u32(smem + OFF_V);
-                const uint32_t td = tmem_base + O_COL;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {                        // two 64-key chunks
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {                            // two 64-key halves, each its own pipeline stage
+                mbar_wait(bar + B_PFULL + c, j & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t pa = smem_u32(smem + OFF_P), va = smem_u32(smem + OFF_V);
+                    const uint32_t td = tmem_base + O_COL;
                     const uint64_t dPh = make_smem_desc(pa + c * TILE16), dPl = make_smem_desc(pa + (2 + c) * TILE16);
                     const uint64_t dVh = make_smem_desc(va + c * TILE8), dVl = make_smem_desc(va + (2 + c) * TILE8);
 #pragma unroll
@@ -237,18 +250,22 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
                             tc_mma(td, dPl + adv, dVh + adv, idO, 1u);
                         }
                     }
+                    tc_commit(bar + B_PEMPTY + c);
+                    if (c == 1) {
+                        tc_commit(bar + B_VEMPTY);
+                        if (j == nb - 1) tc_commit(bar + B_OFULL);
+                    }
                 }
-                tc_commit(bar + B_PEMPTY);
-                tc_commit(bar + B_VEMPTY);
-                if (j == nb - 1) tc_commit(bar + B_OFULL);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
-        // ===== softmax / epilogue warps: thread == query row =====
-        const int q = warp & 3;                    // TMEM lane quarter (warps 2,3,4,5 -> 2,3,0,1)
+        // ===== softmax / epilogue warps: thread == (query row, 64-key half) =====
+        const int q = warp & 3;                    // TMEM lane quarter
+        const int half = (warp - 2) >> 2;          // which 64 keys of every 128-key block (and which 32 columns of O)
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float* red = reinterpret_cast<float*>(smem + OFF_RED);
         float m = -3.0e38f;
         // PASS 1: row maximum of the raw scores
         for (int it = 0; it < nb; ++it) {
@@ -256,10 +273,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             mbar_wait(bar + B_SFULL + s, (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int g2 = 0; g2 < 2; ++g2) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + lane_addr + s * 128 + c * 32, r);
-                const int kbase = it * KT + c * 32;
+                tmem_ld32(tmem_base + lane_addr + s * 128 + half * 64 + g2 * 32, r);
+                const int kbase = it * KT + half * 64 + g2 * 32;
 #pragma unroll
                 for (int e = 0; e < 32; ++e)
                     if (kbase + e < p.Nk) m = fmaxf(m, __uint_as_float(r[e]));
@@ -268,40 +285,49 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(bar + B_SEMPTY + s);
         }
+        red[half * 128 + row] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 softmax warps only
+        m = fmaxf(m, red[(half ^ 1) * 128 + row]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // red[] is reused for the row sums below
         // PASS 2: p = exp2((s - m) * scale*log2e) -> bf16 (hi, lo) written to swizzled smem; row sum
         float l = 0.f;
         const float c1 = p.scale_log2e, c0 = -m * p.scale_log2e;
         for (int j = 0; j < nb; ++j) {
             const int it = nb + j, s = it & 1;
             mbar_wait(bar + B_SFULL + s, (it >> 1) & 1);
-            mbar_wait(bar + B_PEMPTY, (j & 1) ^ 1);            // previous P V product has consumed the P tiles
+            mbar_wait(bar + B_PEMPTY + half, (j & 1) ^ 1);     // the previous P V product has consumed this half's tiles
             tc_fence_after();
+            uint8_t* th = smem + OFF_P + half * TILE16 + row * 128;
+            uint8_t* tl = th + 2 * TILE16;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int g2 = 0; g2 < 2; ++g2) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + lane_addr + s * 128 + c * 32, r);
-                const int kbase = j * KT + c * 32;
-                // key chunk tile (64 keys) and the 16-byte chunks this 32-key group covers inside the 128 B row
-                uint8_t* th = smem + OFF_P + (c >> 1) * TILE16 + row * 128;
-                uint8_t* tl = th + 2 * TILE16;
+                tmem_ld32(tmem_base + lane_addr + s * 128 + half * 64 + g2 * 32, r);
+                const int kbase = j * KT + half * 64 + g2 * 32;
+                // only the last key block can hold padded keys: keep the masking out of the steady-state loop
+                const bool tail = kbase + 32 > p.Nk;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {                  // 8 keys = one 16 B chunk
                     uint32_t hw[4], lw[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int k0 = g * 8 + 2 * e;
-                        float a = exp2f(fmaf(__uint_as_float(r[k0]), c1, c0));
-                        float b = exp2f(fmaf(__uint_as_float(r[k0 + 1]), c1, c0));
-                        if (kbase + k0 >= p.Nk) a = 0.f;
-                        if (kbase + k0 + 1 >= p.Nk) b = 0.f;
+                        float a = ex2_ftz(fmaf(__uint_as_float(r[k0]), c1, c0));
+                        float b = ex2_ftz(fmaf(__uint_as_float(r[k0 + 1]), c1, c0));
+                        if (tail) {
+                            if (kbase + k0 >= p.Nk) a = 0.f;
+                            if (kbase + k0 + 1 >= p.Nk) b = 0.f;
+                        }
                         l += a + b;
-                        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
-                        const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-                        const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
-                        hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
-                        lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+                        // packed split: one cvt.rn.bf16x2 for the hi pair, shift/mask to widen it back, one for the lo pair
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16),
+                                                                        b - __uint_as_float(hb & 0xffff0000u));
+                        hw[e] = hb;
+                        lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
                     }
-                    const int chunk = ((c & 1) * 4 + g) ^ (row & 7);       // SWIZZLE_128B: 16 B chunk index XOR (row % 8)
+                    const int chunk = (g2 * 4 + g) ^ (row & 7);            // SWIZZLE_128B: 16 B chunk index XOR (row % 8)
                     *reinterpret_cast<uint4*>(th + chunk * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     if (x3) *reinterpret_cast<uint4*>(tl + chunk * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
@@ -309,17 +335,20 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             tc_fence_before();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor-core (async) proxy
             __syncwarp();
-            if (lane == 0) { mbar_arrive(bar + B_SEMPTY + s); mbar_arrive(bar + B_PFULL); }
+            if (lane == 0) { mbar_arrive(bar + B_SEMPTY + s); mbar_arrive(bar + B_PFULL + half); }
         }
-        // epilogue: O / l -> bf16 split in [B, Nq, heads*64]
+        red[half * 128 + row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l += red[(half ^ 1) * 128 + row];
+        // epilogue: O / l -> bf16 split in [B, Nq, heads*64]; this warp writes columns [half*32, half*32+32)
         mbar_wait(bar + B_OFULL, 0);
         tc_fence_after();
         const float inv = 1.0f / l;
         const int qrow = q0 + row;
         const int b = bh / p.heads, hh = bh % p.heads;
         const size_t o = ((size_t)b * p.Nq + qrow) * (size_t)(p.heads * HD) + (size_t)hh * HD;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        {
+            const int c = half;
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_addr + O_COL + c * 32, r);
             if (qrow < p.Nq) {
