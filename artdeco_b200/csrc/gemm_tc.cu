@@ -56,6 +56,13 @@ struct GemmParams {
     long long sD2, sO2, sR2;
     // conv mode (conv_wb > 0): M tile = conv_hb x conv_wb pixel rectangle of an H x W image, K block = (tap, chunk)
     int conv_wb, conv_hb, conv_H, conv_W, conv_chunks, conv_tiles_x, conv_tiles_y;
+    // RoPE epilogue (rope_ndst > 0): output columns [0, rope_ndst * rope_C) are attention heads (64 wide); each is rotated
+    // with RoPE2D for its token's (y, x) position and written as a bf16 split in head-major layout [B*heads, ntok, 64] to
+    // rope_hi/lo[col / rope_C]; the remaining columns take the ordinary D path (D is pre-shifted by the caller).
+    int rope_ndst, rope_C, rope_heads, rope_ntok, rope_npos;
+    const long long* rope_pos;      // int64 [M, 2] (y, x)
+    const float* rope_table;        // [n_pos][16][2] (cos, sin)
+    __nv_bfloat16* rope_hi[2]; __nv_bfloat16* rope_lo[2];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,6 +166,9 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
     return c;
 }
 
+// ROPE: the epilogue variant of adb_gemm_bf16_rope (own instantiation so that its extra live values do not cost the plain
+// GEMM registers); it has no residual / activation / split-output paths.
+template <bool ROPE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
@@ -333,17 +343,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             for (int g = 0; g < 2; ++g) {
                 const int c0 = n0 + g * 32;
                 if (c0 >= p.N) continue;
-                float v[32];
+                float (&v)[32] = acc[g];      // finished accumulators are transformed in place
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float t = acc[g][j] * p.alpha;
                     if (p.bias && c0 + j < p.N) t += __ldg(p.bias + c0 + j);
-                    if (p.act == 1) t = gelu_erf(t);
-                    else if (p.act == 2) t = fmaxf(t, 0.f);
+                    if (!ROPE) {
+                        if (p.act == 1) t = gelu_erf(t);
+                        else if (p.act == 2) t = fmaxf(t, 0.f);
+                    }
                     v[j] = t;
                 }
+                if (ROPE && c0 < p.rope_ndst * p.rope_C) {
+                    // this thread holds dims [d0, d0+32) of one head of token `row`: one RoPE axis (y: d0 = 0, x: d0 = 32),
+                    // pairs (i, i+16) -- blocks.py:101-103 / pos_embed.py:129-159, fused with the head split
+                    const int sec = c0 / p.rope_C, cc = c0 - sec * p.rope_C;
+                    const int hh = cc >> 6, axis = (cc >> 5) & 1;
+                    long long pz = __ldg(p.rope_pos + row * 2 + axis);
+                    pz = pz < 0 ? 0 : (pz >= p.rope_npos ? p.rope_npos - 1 : pz);
+                    const float4* tb = reinterpret_cast<const float4*>(p.rope_table + pz * 32);
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const float4 cs = __ldg(tb + i4);          // (cos, sin) of frequencies 2*i4 and 2*i4+1
+                        const int i = 2 * i4;
+                        const float u0 = v[i], w0 = v[i + 16], u1 = v[i + 1], w1 = v[i + 17];
+                        v[i] = u0 * cs.x - w0 * cs.y;      v[i + 16] = w0 * cs.x + u0 * cs.y;
+                        v[i + 1] = u1 * cs.z - w1 * cs.w;  v[i + 17] = w1 * cs.z + u1 * cs.w;
+                    }
+                    const long long bq = row / p.rope_ntok, nq = row - bq * p.rope_ntok;
+                    const size_t off = (((size_t)bq * p.rope_heads + hh) * p.rope_ntok + nq) * 64 + axis * 32;
+                    __nv_bfloat16* hp = p.rope_hi[sec] + off;
+                    __nv_bfloat16* lp = p.rope_lo[sec] ? p.rope_lo[sec] + off : nullptr;
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {               // 16 values -> one 32-byte store of hi and of lo
+                        uint32_t hw[8], lw[8];
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; ++k2) {
+                            const float a = v[16 * h8 + 2 * k2], b = v[16 * h8 + 2 * k2 + 1];
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16),
+                                                                            b - __uint_as_float(hb & 0xffff0000u));
+                            hw[k2] = hb;
+                            lw[k2] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        st_v8_b32(hp + 16 * h8, hw);
+                        if (lp) st_v8_b32(lp + 16 * h8, lw);
+                    }
+                    continue;
+                }
                 if (vec_ok && c0 + 32 <= p.N) {
-                    if (p.residual) {
+                    if (!ROPE && p.residual) {
                         const float* rp = p.residual + rbase + (size_t)row * p.ldr + c0;
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
@@ -358,23 +408,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) st_v8(dp + 8 * j8, v + 8 * j8);
                     }
-                    if (p.Dhi) {
-                        uint32_t hw[16], lw[16];
-#pragma unroll
-                        for (int k2 = 0; k2 < 16; ++k2) {
-                            float a = v[2 * k2], b = v[2 * k2 + 1];
-                            if (p.split_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-                            const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-                            const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-                            hw[k2] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-                            lw[k2] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-                        }
+                    if (!ROPE && p.Dhi) {
                         __nv_bfloat16* hp = p.Dhi + obase + (size_t)row * p.ldo + c0;
-                        st_v8_b32(hp, hw); st_v8_b32(hp + 16, hw + 8);
-                        if (p.Dlo) {
-                            __nv_bfloat16* lp = p.Dlo + obase + (size_t)row * p.ldo + c0;
-                            st_v8_b32(lp, lw); st_v8_b32(lp + 16, lw + 8);
+                        __nv_bfloat16* lp = p.Dlo ? p.Dlo + obase + (size_t)row * p.ldo + c0 : nullptr;
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            uint32_t hw[8], lw[8];
+#pragma unroll
+                            for (int k2 = 0; k2 < 8; ++k2) {
+                                float a = v[16 * h8 + 2 * k2], b = v[16 * h8 + 2 * k2 + 1];
+                                if (p.split_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                                const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16),
+                                                                                b - __uint_as_float(hb & 0xffff0000u));
+                                hw[k2] = hb;
+                                lw[k2] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
+                            st_v8_b32(hp + 16 * h8, hw);
+                            if (lp) st_v8_b32(lp + 16 * h8, lw);
                         }
                     }
                 } else {
@@ -382,9 +434,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     for (int j = 0; j < 32; ++j) {
                         if (c0 + j < p.N) {
                             float t = v[j];
-                            if (p.residual) t += __ldg(p.residual + rbase + (size_t)row * p.ldr + c0 + j);
+                            if (!ROPE && p.residual) t += __ldg(p.residual + rbase + (size_t)row * p.ldr + c0 + j);
                             if (p.D) p.D[dbase + (size_t)row * p.ldd + c0 + j] = t;
-                            if (p.Dhi) {
+                            if (!ROPE && p.Dhi) {
                                 const float ts = p.split_relu ? fmaxf(t, 0.f) : t;
                                 const __nv_bfloat16 h = __float2bfloat16_rn(ts);
                                 p.Dhi[obase + (size_t)row * p.ldo + c0 + j] = h;
@@ -465,10 +517,12 @@ int launch(const CUtensorMap& mAhi, const CUtensorMap& mAlo, const CUtensorMap& 
         int dev = 0;
         ADB_CUDA(cudaGetDevice(&dev));
         ADB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        ADB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        ADB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        ADB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     }
     const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
-    gemm_tc_kernel<<<grid, NTHREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, p);
+    if (p.rope_ndst > 0) gemm_tc_kernel<true><<<grid, NTHREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, p);
+    else gemm_tc_kernel<false><<<grid, NTHREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, p);
     ADB_CHECK_LAUNCH("gemm_tc_kernel");
     return ADB_OK;
 }
@@ -512,6 +566,54 @@ ADB_API int adb_gemm_bf16(int batch, int M, int N, int K, const void* A_hi, cons
     p.zdiv = zdiv > 0 ? zdiv : (1 << 30); p.sD2 = sD2; p.sO2 = sO2; p.sR2 = sR2;
     p.conv_wb = 0;
     const long long tiles = (long long)adb_cdiv(M, BM) * adb_cdiv(N, BN) * batch;
+    return launch(mAhi, mAlo, mBhi, mBlo, p, tiles, stream);
+}
+
+// Linear layer whose leading output columns are attention heads: y = A W^T + bias with
+//   columns [0, n_rope_dst*C)   (C = heads*64)  rotated by RoPE2D (table lookup by the token's (y,x) position), split into
+//                               bf16 (hi, lo) and written head-major [B*heads, ntok, 64] to q (section 0) / k (section 1);
+//   columns [n_rope_dst*C, N)   written as plain fp32 to D[row * ldd + (col - n_rope_dst*C)]  (the V projection).
+// Replaces  qkv = Linear(x); q, k = rope(q), rope(k)  (croco/models/blocks.py:94-103, 150-160) + the head transposes:
+// the [rows, 3C] fp32 tensor is never written.  M = B * ntok rows.
+ADB_API int adb_gemm_bf16_rope(int M, int N, int K, const void* A_hi, const void* A_lo, long long lda, const void* B_hi,
+                               const void* B_lo, long long ldb, const float* bias, int ntok, int heads, int n_rope_dst,
+                               const long long* pos, const float* table, int n_pos, void* q_hi, void* q_lo, void* k_hi,
+                               void* k_lo, float* D_tail, long long ldd, cudaStream_t stream) {
+    ADB_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ntok >= 1 && heads >= 1 && M % ntok == 0, "adb_gemm_bf16_rope: bad sizes");
+    ADB_REQUIRE(n_rope_dst == 1 || n_rope_dst == 2, "adb_gemm_bf16_rope: n_rope_dst must be 1 or 2");
+    const int C = heads * 64;
+    ADB_REQUIRE(N >= n_rope_dst * C, "adb_gemm_bf16_rope: N smaller than the rotated sections");
+    ADB_REQUIRE(A_hi && B_hi && pos && table && n_pos >= 1 && q_hi && (n_rope_dst == 1 || k_hi), "adb_gemm_bf16_rope: null pointer");
+    ADB_REQUIRE((N == n_rope_dst * C) || D_tail, "adb_gemm_bf16_rope: tail columns need D_tail");
+    ADB_REQUIRE((A_lo == nullptr) == (B_lo == nullptr), "adb_gemm_bf16_rope: A_lo and B_lo must be given together");
+    ADB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "adb_gemm_bf16_rope: strides must be multiples of 8 elements");
+    ADB_REQUIRE(((uintptr_t)A_hi % 16 == 0) && ((uintptr_t)B_hi % 16 == 0) && ((uintptr_t)table % 16 == 0) &&
+                (((uintptr_t)q_hi | (uintptr_t)q_lo | (uintptr_t)k_hi | (uintptr_t)k_lo) % 32 == 0),
+                "adb_gemm_bf16_rope: operands must be 16-byte (outputs 32-byte) aligned");
+    GemmParams p{};
+    p.nterms = A_lo ? 3 : 1;
+    CUtensorMap mAhi, mAlo, mBhi, mBlo;
+    int rc;
+    if ((rc = make_map(&mAhi, A_hi, M, K, lda, 0, 1))) return rc;
+    if ((rc = make_map(&mBhi, B_hi, N, K, ldb, 0, 1))) return rc;
+    mAlo = mAhi; mBlo = mBhi;
+    if (p.nterms == 3) {
+        if ((rc = make_map(&mAlo, A_lo, M, K, lda, 0, 1))) return rc;
+        if ((rc = make_map(&mBlo, B_lo, N, K, ldb, 0, 1))) return rc;
+    }
+    p.M = M; p.N = N; p.K = K; p.batch = 1;
+    p.D = D_tail ? D_tail - (long long)n_rope_dst * C : nullptr;   // column c of the GEMM lands at D_tail[c - n_rope_dst*C]
+    p.ldd = ldd; p.sD = 0;
+    p.Dhi = nullptr; p.Dlo = nullptr; p.ldo = N; p.sO = 0;
+    p.bias = bias; p.residual = nullptr; p.ldr = N; p.sR = 0;
+    p.alpha = 1.0f; p.act = 0; p.split_relu = 0;
+    p.zdiv = 1 << 30; p.sD2 = p.sO2 = p.sR2 = 0;
+    p.conv_wb = 0;
+    p.rope_ndst = n_rope_dst; p.rope_C = C; p.rope_heads = heads; p.rope_ntok = ntok; p.rope_npos = n_pos;
+    p.rope_pos = pos; p.rope_table = table;
+    p.rope_hi[0] = (__nv_bfloat16*)q_hi; p.rope_lo[0] = (__nv_bfloat16*)q_lo;
+    p.rope_hi[1] = (__nv_bfloat16*)k_hi; p.rope_lo[1] = (__nv_bfloat16*)k_lo;
+    const long long tiles = (long long)adb_cdiv(M, BM) * adb_cdiv(N, BN);
     return launch(mAhi, mAlo, mBhi, mBlo, p, tiles, stream);
 }
 

@@ -46,6 +46,8 @@ class AsymmetricMASt3R:
         self.x3 = precision == "bf16x3"
         import os
         self._fused_attn = os.environ.get("ADB_ATTN", "fused") != "materialized"
+        # RoPE + head split in the qkv / projq / projkv GEMM epilogue (ADB_ROPE=separate keeps the standalone kernel for A/B)
+        self._fused_rope = os.environ.get("ADB_ROPE", "fused") != "separate"
         self.patch_embed = _PatchEmbedInfo(16)
         self.device = torch.device("cpu")
         self._sd = None          # fp32 tensors (LN params, biases, conv weights)
@@ -159,11 +161,17 @@ class AsymmetricMASt3R:
         """x fp32 [B,N,C] -> x + proj(attn(norm1(x)))  (blocks.py:94-112,128)"""
         B, N, C = x.shape
         _, xn = self._ln(x, pre + ".norm1")
-        qkv, _ = self._linear(xn, pre + ".attn.qkv", B * N)
         Npad = _roundup(N, 8)
-        q = ops.rope_heads(qkv, B, N, h, 3 * C, 0, pos, 0, x3=self.x3)
-        k = ops.rope_heads(qkv, B, N, h, 3 * C, C, pos, 0, x3=self.x3)
-        vt = ops.rope_heads(qkv, B, N, h, 3 * C, 2 * C, None, 2, x3=self.x3, Npad=Npad)
+        if self._fused_rope:
+            # q, k leave the qkv GEMM already rotated, head-major and split; only V (fp32 [B*N, C]) is written plainly
+            q, k, v = ops.linear_rope(xn, self._w[pre + ".attn.qkv.weight"], self._sd.get(pre + ".attn.qkv.bias"), B, N, h,
+                                      pos, 2, x3=self.x3)
+            vt = ops.rope_heads(v, B, N, h, C, 0, None, 2, x3=self.x3, Npad=Npad)
+        else:
+            qkv, _ = self._linear(xn, pre + ".attn.qkv", B * N)
+            q = ops.rope_heads(qkv, B, N, h, 3 * C, 0, pos, 0, x3=self.x3)
+            k = ops.rope_heads(qkv, B, N, h, 3 * C, C, pos, 0, x3=self.x3)
+            vt = ops.rope_heads(qkv, B, N, h, 3 * C, 2 * C, None, 2, x3=self.x3, Npad=Npad)
         o = self._attn_core(q, k, vt, B, h, N, N, Npad)
         out, _ = self._linear(o, pre + ".attn.proj", B * N, residual=x.reshape(B * N, C))
         return out.view(B, N, C)
@@ -186,12 +194,19 @@ class AsymmetricMASt3R:
         x = self._self_attention(x, xpos, pre, h)
         _, yn = self._ln(y, pre + ".norm_y")
         _, xn = self._ln(x, pre + ".norm2")
-        qf, _ = self._linear(xn, pre + ".cross_attn.projq", B * N)
-        kv, _ = self._linear(yn, pre + ".cross_attn.projkv", B * Nk)
         Nkpad = _roundup(Nk, 8)
-        q = ops.rope_heads(qf, B, N, h, C, 0, xpos, 0, x3=self.x3)
-        k = ops.rope_heads(kv, B, Nk, h, 2 * C, 0, ypos, 0, x3=self.x3)
-        vt = ops.rope_heads(kv, B, Nk, h, 2 * C, C, None, 2, x3=self.x3, Npad=Nkpad)
+        if self._fused_rope:
+            q, _, _ = ops.linear_rope(xn, self._w[pre + ".cross_attn.projq.weight"],
+                                      self._sd.get(pre + ".cross_attn.projq.bias"), B, N, h, xpos, 1, x3=self.x3)
+            k, _, v = ops.linear_rope(yn, self._w[pre + ".cross_attn.projkv.weight"],
+                                      self._sd.get(pre + ".cross_attn.projkv.bias"), B, Nk, h, ypos, 1, x3=self.x3)
+            vt = ops.rope_heads(v, B, Nk, h, C, 0, None, 2, x3=self.x3, Npad=Nkpad)
+        else:
+            qf, _ = self._linear(xn, pre + ".cross_attn.projq", B * N)
+            kv, _ = self._linear(yn, pre + ".cross_attn.projkv", B * Nk)
+            q = ops.rope_heads(qf, B, N, h, C, 0, xpos, 0, x3=self.x3)
+            k = ops.rope_heads(kv, B, Nk, h, 2 * C, 0, ypos, 0, x3=self.x3)
+            vt = ops.rope_heads(kv, B, Nk, h, 2 * C, C, None, 2, x3=self.x3, Npad=Nkpad)
         o = self._attn_core(q, k, vt, B, h, N, Nk, Nkpad)
         x2, _ = self._linear(o, pre + ".cross_attn.proj", B * N, residual=x.reshape(B * N, C))
         return self._mlp(x2.view(B, N, C), pre + ".norm3", pre + ".mlp")

@@ -121,6 +121,34 @@ def rope_heads(x: torch.Tensor, B, N, h, ld, col0, pos, mode: int, base: float =
     return Split(hi, lo)
 
 
+_lib.register("adb_gemm_bf16_rope", [i32, i32, i32, vp, vp, i64, vp, vp, i64, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp,
+                                     vp, i64, vp])
+
+
+def linear_rope(a: Split, w: Split, bias, B: int, N: int, h: int, pos, n_dst: int, x3=True, base: float = 100.0,
+                n_pos: int = 64):
+    """Linear + RoPE2D + head split in the GEMM epilogue (adb_gemm_bf16_rope).  The weight's first ``n_dst * h*64`` output
+    rows are attention heads (q, then k); returns (q Split [B,h,N,64], k Split | None, tail fp32 [B*N, rest] | None)."""
+    Nout, K = w.hi.shape
+    C = h * 64
+    dev = a.hi.device
+    def heads():
+        return Split(torch.empty(B, h, N, 64, dtype=BF16, device=dev),
+                     torch.empty(B, h, N, 64, dtype=BF16, device=dev) if x3 else None)
+    q = heads()
+    k = heads() if n_dst == 2 else None
+    rest = Nout - n_dst * C
+    tail = torch.empty(B * N, rest, dtype=torch.float32, device=dev) if rest > 0 else None
+    table = rope_table(n_pos, dev, base)
+    use3 = a.lo is not None and w.lo is not None
+    _lib.call("adb_gemm_bf16_rope", B * N, Nout, K, _lib.ptr(a.hi), _lib.ptr(a.lo) if use3 else None, K,
+              _lib.ptr(w.hi), _lib.ptr(w.lo) if use3 else None, K, _lib.ptr(bias) if bias is not None else None, N, h, n_dst,
+              _lib.ptr(pos, torch.int64), _lib.ptr(table), n_pos, _lib.ptr(q.hi), _lib.ptr(q.lo),
+              _lib.ptr(k.hi) if k is not None else None, _lib.ptr(k.lo) if k is not None else None,
+              _lib.ptr(tail) if tail is not None else None, max(rest, 1), _lib.stream())
+    return q, k, tail
+
+
 def softmax_rows(s: torch.Tensor, rows: int, L: int, ld_in: int, x3=True) -> Split:
     dev = s.device
     hi = torch.empty(rows, L, dtype=BF16, device=dev)

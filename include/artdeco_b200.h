@@ -205,6 +205,15 @@ int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, const void* 
 int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
                   void* y_hi, void* y_lo, adb_stream_t stream);
 int adb_split_bf16(long long n, const float* x, void* hi, void* lo, adb_stream_t stream);
+/* Linear layer fused with RoPE2D + head split (croco/models/blocks.py:94-103 self-attention qkv, :150-160 cross-attention
+ * projq / projk): y = A W^T + bias, M = B*ntok rows; output columns [0, n_rope_dst*heads*64) are rotated per head with the
+ * (cos, sin) table row of the token's (y,x) position and written as bf16 (hi, lo) head-major [B*heads, ntok, 64] to q (first
+ * heads*64 columns) and k (next heads*64, n_rope_dst == 2); the remaining columns go to D_tail fp32 [M, ldd] (the V projection).
+ * The [M, N] fp32 projection is never written.  table: float [n_pos][16][2] (cos, sin), 16-byte aligned. */
+int adb_gemm_bf16_rope(int M, int N, int K, const void* A_hi, const void* A_lo, long long lda, const void* B_hi,
+                       const void* B_lo, long long ldb, const float* bias, int ntok, int heads, int n_rope_dst,
+                       const long long* pos /*[M,2] int64 (y,x)*/, const float* table, int n_pos, void* q_hi, void* q_lo,
+                       void* k_hi, void* k_lo, float* D_tail, long long ldd, adb_stream_t stream);
 /* curope.rope_2d(tokens[B,N,H,D] fp32 IN PLACE, positions[B,N,2] int64 (y,x), base, F0) — curope.cpp:49-68, kernels.cu:18-108.
  * tokens: stride(3) == 1 and stride(2) == D as the reference checks (kernels.cu:91); stride_b / stride_n in elements.
  * F0 = -1 applies the inverse rotation (the reference's backward, curope2d.py:25-29). */

@@ -104,3 +104,39 @@ def test_fused_attention_matches_fp64(cuda, B, h, Nq, Nk):
     o = ops.attention(ops.split(q), ops.split(k), ops.split(vt), B, h, Nq, Nk, Nkpad, 0.125)
     ref = (torch.softmax(0.125 * q.double() @ k.double().transpose(-1, -2), -1) @ v.double()).permute(0, 2, 1, 3).reshape(B * Nq, h * 64)
     assert rel_err(o.hi.float() + o.lo.float(), ref) < 3e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,h,n_dst,tail", [(2, 200, 4, 2, True), (1, 1024, 16, 2, True), (3, 77, 2, 1, False), (2, 130, 12, 1, True)])
+def test_gemm_rope_epilogue_matches_separate_kernels(cuda, B, N, h, n_dst, tail):
+    """adb_gemm_bf16_rope (Linear + RoPE2D + head split in the epilogue) against Linear (adb_gemm_bf16) followed by the
+    standalone adb_rope_heads kernel, and against the fp64 PyTorch formulation (oracle/mast3r_torch.py:rope2d)."""
+    from artdeco_b200.mast3r import ops
+    from oracle import mast3r_torch as mt
+    g = torch.Generator().manual_seed(0)
+    C = h * 64
+    K = 192
+    Nout = n_dst * C + (C if tail else 0)
+    x = torch.randn(B * N, K, generator=g)
+    w = torch.randn(Nout, K, generator=g) / K ** 0.5
+    bias = torch.randn(Nout, generator=g)
+    pos = torch.stack([torch.randint(0, 40, (B, N), generator=g), torch.randint(0, 64, (B, N), generator=g)], -1).to(cuda)
+    a, ws = ops.split(x.to(cuda)), ops.split(w.to(cuda))
+    q, k, v = ops.linear_rope(a, ws, bias.to(cuda), B, N, h, pos, n_dst)
+    full, _ = ops.linear(a, ws, bias.to(cuda), B * N)
+    q_ref = ops.rope_heads(full, B, N, h, Nout, 0, pos, 0)
+    # both sides are 16-bit (hi+lo) roundings of fp32 values that may differ in the last ulp: 2^-16 granularity
+    assert rel_err(q.hi.float() + q.lo.float(), q_ref.hi.float() + q_ref.lo.float()) < 2e-5
+    if n_dst == 2:
+        k_ref = ops.rope_heads(full, B, N, h, Nout, C, pos, 0)
+        assert rel_err(k.hi.float() + k.lo.float(), k_ref.hi.float() + k_ref.lo.float()) < 2e-5
+    else:
+        assert k is None
+    if tail:
+        assert v.shape == (B * N, C) and rel_err(v, full[:, n_dst * C:]) < 1e-6
+    else:
+        assert v is None
+    # fp64 reference of the whole thing
+    y = (x.double() @ w.double().T + bias.double()).view(B, N, -1)
+    qd = y[..., :C].reshape(B, N, h, 64).transpose(1, 2)
+    assert rel_err(q.hi.float() + q.lo.float(), mt.rope2d(qd, pos.cpu(), base=100.0)) < 3e-5
