@@ -7,7 +7,7 @@
 // the reference runs as three torch kernels with a [B,h,N,N] fp32 tensor written and read twice.
 //
 // Structure (head_dim = 64, keys processed in blocks of 128):
-//   TMA producer warp     Q tile once; K blocks through a 2-stage ring (read twice: see below); V^T blocks (1 stage)
+//   TMA producer warp     Q tile once; K blocks through a 2-stage ring (read twice: see below); V^T blocks through a 2-stage ring
 //   MMA warp (1 thread)   S_j = Q K_j^T  (tcgen05.mma M128 N128 K16, bf16x3 = 12 MMAs) into one of two TMEM S buffers;
 //                         O += P_j V_j   (M128 N64 K16, bf16x3 = 24 MMAs) into a TMEM O accumulator
 //   8 softmax warps       two warps per TMEM lane quarter: thread == (query row, 64-key half of each key block).
@@ -125,14 +125,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // shared memory map (bytes, 1024-aligned tiles)
 constexpr int OFF_Q = 0;                       // Q hi, Q lo            2 x 16 KB
 constexpr int OFF_K = OFF_Q + 2 * TILE16;      // 2 stages x (K hi, K lo)   64 KB
-constexpr int OFF_V = OFF_K + 4 * TILE16;      // V^T: 2 key-chunks x (hi, lo) x 8 KB = 32 KB
-constexpr int OFF_P = OFF_V + 4 * TILE8;       // P: 2 key-chunks x (hi, lo) x 16 KB = 64 KB
+constexpr int OFF_V = OFF_K + 4 * TILE16;      // V^T: 2 stages x [2 key-chunks x (hi, lo) x 8 KB] = 64 KB
+constexpr int OFF_P = OFF_V + 8 * TILE8;       // P: 2 key-chunks x (hi, lo) x 16 KB = 64 KB
 constexpr int OFF_BAR = OFF_P + 4 * TILE16;    // barriers
 constexpr int OFF_RED = OFF_BAR + 256;         // [2 halves][128 rows] floats: row max / row sum exchange
 constexpr int SMEM_BYTES = OFF_RED + 2 * 128 * 4 + 1024;
 
-enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 6, B_SFULL = 7, B_SEMPTY = 9, B_PFULL = 11,
-       B_PEMPTY = 13, B_OFULL = 15, B_COUNT = 16 };
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11, B_PFULL = 13,
+       B_PEMPTY = 15, B_OFULL = 17, B_COUNT = 18 };
 
 __global__ void __launch_bounds__(NT, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo,
@@ -156,8 +156,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             mbar_init(bar + B_KFULL + s, 1); mbar_init(bar + B_KEMPTY + s, 1);
             mbar_init(bar + B_SFULL + s, 1); mbar_init(bar + B_SEMPTY + s, 8);
             mbar_init(bar + B_PFULL + s, 4); mbar_init(bar + B_PEMPTY + s, 1);
+            mbar_init(bar + B_VFULL + s, 1); mbar_init(bar + B_VEMPTY + s, 1);
         }
-        mbar_init(bar + B_VFULL, 1); mbar_init(bar + B_VEMPTY, 1);
         mbar_init(bar + B_OFULL, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -184,15 +184,16 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
                 mbar_expect_tx(bar + B_KFULL + s, lo ? kstage_bytes : (uint32_t)TILE16);
                 tma_load_3d(st, &mKhi, bar + B_KFULL + s, 0, j * KT, bh);
                 if (lo) tma_load_3d(st + TILE16, &mKlo, bar + B_KFULL + s, 0, j * KT, bh);
-                if (it >= nb) {                            // pass 2: the matching V^T block (two 64-key chunks)
-                    mbar_wait(bar + B_VEMPTY, (j & 1) ^ 1);
-                    mbar_expect_tx(bar + B_VFULL, v_bytes);
-                    uint8_t* vt = smem + OFF_V;
-                    tma_load_3d(vt, &mVhi, bar + B_VFULL, j * KT, 0, bh);
-                    tma_load_3d(vt + TILE8, &mVhi, bar + B_VFULL, j * KT + 64, 0, bh);
+                if (it >= nb) {                            // pass 2: the matching V^T block (two 64-key chunks), 2-stage ring
+                    const int vs = j & 1;
+                    mbar_wait(bar + B_VEMPTY + vs, ((j >> 1) & 1) ^ 1);
+                    mbar_expect_tx(bar + B_VFULL + vs, v_bytes);
+                    uint8_t* vt = smem + OFF_V + vs * 4 * TILE8;
+                    tma_load_3d(vt, &mVhi, bar + B_VFULL + vs, j * KT, 0, bh);
+                    tma_load_3d(vt + TILE8, &mVhi, bar + B_VFULL + vs, j * KT + 64, 0, bh);
                     if (x3) {
-                        tma_load_3d(vt + 2 * TILE8, &mVlo, bar + B_VFULL, j * KT, 0, bh);
-                        tma_load_3d(vt + 3 * TILE8, &mVlo, bar + B_VFULL, j * KT + 64, 0, bh);
+                        tma_load_3d(vt + 2 * TILE8, &mVlo, bar + B_VFULL + vs, j * KT, 0, bh);
+                        tma_load_3d(vt + 3 * TILE8, &mVlo, bar + B_VFULL + vs, j * KT + 64, 0, bh);
                     }
                 }
             }
@@ -231,13 +232,14 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
         issue_S(nb, true);                                           // first S of pass 2
         for (int j = 0; j < nb; ++j) {
             if (j + 1 < nb) issue_S(nb + j + 1, true);               // overlap the next S with this block's softmax
-            mbar_wait(bar + B_VFULL, j & 1);
+            const int vs = j & 1;
+            mbar_wait(bar + B_VFULL + vs, (j >> 1) & 1);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {                            // two 64-key halves, each its own pipeline stage
                 mbar_wait(bar + B_PFULL + c, j & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t pa = smem_u32(smem + OFF_P), va = smem_u32(smem + OFF_V);
+                    const uint32_t pa = smem_u32(smem + OFF_P), va = smem_u32(smem + OFF_V + vs * 4 * TILE8);
                     const uint32_t td = tmem_base + O_COL;
                     const uint64_t dPh = make_smem_desc(pa + c * TILE16), dPl = make_smem_desc(pa + (2 + c) * TILE16);
                     const uint64_t dVh = make_smem_desc(va + c * TILE8), dVl = make_smem_desc(va + (2 + c) * TILE8);
@@ -252,7 +254,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
                     }
                     tc_commit(bar + B_PEMPTY + c);
                     if (c == 1) {
-                        tc_commit(bar + B_VEMPTY);
+                        tc_commit(bar + B_VEMPTY + vs);
                         if (j == nb - 1) tc_commit(bar + B_OFULL);
                     }
                 }

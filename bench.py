@@ -204,7 +204,7 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_cpu):
     ms = timed(step, k, max(3, warmup))
     ms_e2e = timed(e2e_step, k, 3)
     # live duration of the dominant kernel (the tcgen05 GEMM / conv kernel) over one step
-    for name in ("adb_gemm_bf16", "adb_conv3x3_bf16", "adb_attention_bf16", "adb_layernorm", "adb_split_bf16",
+    for name in ("adb_gemm_bf16", "adb_gemm_bf16_rope", "adb_conv3x3_bf16", "adb_attention_bf16", "adb_layernorm", "adb_split_bf16",
                  "adb_rope_heads", "adb_softmax_rows", "adb_im2col_patch16"):
         _lib.LAUNCHES.setdefault(name, 1)
     _lib.TIMER = _lib.StageTimer()
@@ -215,7 +215,7 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_cpu):
     tot = _lib.TIMER.totals_ms()
     launches = _lib.TIMER.launches
     _lib.TIMER = None
-    gemm_ms = sum(tot.get(n, (0.0, 0))[0] for n in ("adb_gemm_bf16", "adb_conv3x3_bf16", "adb_attention_bf16"))
+    gemm_ms = sum(tot.get(n, (0.0, 0))[0] for n in ("adb_gemm_bf16", "adb_gemm_bf16_rope", "adb_conv3x3_bf16", "adb_attention_bf16"))
     pairs_s = world * B / (ms * 1e-3)
     peaks = {}
     pth = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -84,7 +84,7 @@ if __name__ == "__main__":
         print(f"[{prec} B={B}] CUDA-graph replay: {a.elapsed_time(b) / 10:.2f} ms -> {B / (a.elapsed_time(b) / 10) * 1e3:.2f} pairs/s")
     if os.environ.get("ADB_STAGE"):
         _lib.TIMER = _lib.StageTimer()
-        _lib.LAUNCHES.update({k: 1 for k in ("adb_gemm_bf16", "adb_layernorm", "adb_split_bf16", "adb_rope_heads",
+        _lib.LAUNCHES.update({k: 1 for k in ("adb_gemm_bf16", "adb_gemm_bf16_rope", "adb_layernorm", "adb_split_bf16", "adb_rope_heads",
                                              "adb_softmax_rows", "adb_im2col_patch16")})
         forward_pair(m, img1, img2)
         torch.cuda.synchronize()
