@@ -7,17 +7,21 @@
 // the reference runs as three torch kernels with a [B,h,N,N] fp32 tensor written and read twice.
 //
 // Structure (head_dim = 64, keys processed in blocks of 128):
-//   TMA producer warp     Q tile once; K blocks through a 2-stage ring (read twice: see below); V^T blocks through a 2-stage ring
+//   TMA producer warps    Q tile once; K blocks through a 3-stage ring (read twice: see below); V^T blocks through a 3-stage
+//                         ring from a second producer warp.  The loads are LATENCY-bound (~1 us per 32 KB block from L2): with
+//                         every MMA and all of the softmax arithmetic removed the kernel ran only 15 % faster, so ring depth,
+//                         not math, sets the speed
 //   MMA warp (1 thread)   S_j = Q K_j^T  (tcgen05.mma M128 N128 K16, bf16x3 = 12 MMAs) into one of two TMEM S buffers;
 //                         O += P_j V_j   (M128 N64 K16, bf16x3 = 24 MMAs) into a TMEM O accumulator
 //   8 softmax warps       two warps per TMEM lane quarter: thread == (query row, 64-key half of each key block).
 //                         PASS 1 reads every S_j (computed from the bf16 HI parts only: the subtracted maximum only has to
 //                         be close to the true one, softmax is invariant to it) and keeps the row maximum.  PASS 2 recomputes
-//                         S_j in bf16x3, forms p = exp2((s - max) * scale*log2e), accumulates the row sum, and writes its
-//                         64-key half of P_j as a bf16 (hi, lo) pair straight into shared memory in the 128-byte-swizzled
-//                         K-major layout the UMMA descriptor expects — the A operand of the P V product.  The two halves are
-//                         independent pipeline stages (own full/empty barriers): P V of one half overlaps the exponentials
-//                         of the other and of the next block.
+//                         S_j in bf16x3, forms p = exp2((s - max) * scale*log2e), accumulates the row sum, and stores its
+//                         64-key half of P_j as packed bf16 (hi, lo) words back into TENSOR MEMORY, over the very columns
+//                         the scores came from (tcgen05.st): P V is a TS-MMA (A operand from TMEM, B = V^T from smem), so P
+//                         costs no shared-memory write, no proxy fence and no operand read bandwidth.  The two halves are
+//                         independent pipeline stages (own full barrier): P V of one half overlaps the exponentials of the
+//                         other and of the next block; an S/P buffer is recycled when the P V products that read it retire.
 //   Two passes instead of an online-softmax rescale: the running-max correction would need a TMEM read-modify-write of O
 //   per key block; recomputing Q K^T costs 12 extra MMAs per block and keeps O a pure accumulate chain.
 // Precision: bf16x3 everywhere (same contract as csrc/gemm_tc.cu); exp via ex2.approx (2 ulp).
@@ -25,10 +29,12 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
-constexpr int NT = 320;                  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..9 softmax
+constexpr int NT = 352;                  // warp 0 TMA (Q, K), warp 1 MMA (+TMEM alloc), warps 2..9 softmax, warp 10 TMA (V)
+constexpr int KST = 3, VST = 3;          // K / V ring depths: loads are latency-bound (~1 us), keep 3 blocks in flight
 constexpr int QT = 128, KT = 128, HD = 64;
 constexpr int TILE16 = 128 * 64 * 2;     // [128 rows x 64 cols] bf16 = 16 KB
 constexpr int TILE8 = 64 * 64 * 2;       // [64 rows x 64 cols] bf16 = 8 KB
@@ -40,6 +46,7 @@ struct AttnParams {
     float scale_log2e;
     __nv_bfloat16* Ohi; __nv_bfloat16* Olo;   // [B, Nq, heads*64]
     int nterms;
+    int dbg;   // diagnostic switches (ADB_ATTN_DBG): 1 no ex2, 2 no lo split, 4 no tmem store, 8 no pass-1 max
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,6 +84,14 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand from TENSOR MEMORY (128 lanes x 8 columns per K=16 step, two bf16 per 32-bit column, k even in the low half)
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -122,17 +137,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
 // shared memory map (bytes, 1024-aligned tiles)
 constexpr int OFF_Q = 0;                       // Q hi, Q lo            2 x 16 KB
-constexpr int OFF_K = OFF_Q + 2 * TILE16;      // 2 stages x (K hi, K lo)   64 KB
-constexpr int OFF_V = OFF_K + 4 * TILE16;      // V^T: 2 stages x [2 key-chunks x (hi, lo) x 8 KB] = 64 KB
-constexpr int OFF_P = OFF_V + 8 * TILE8;       // P: 2 key-chunks x (hi, lo) x 16 KB = 64 KB
-constexpr int OFF_BAR = OFF_P + 4 * TILE16;    // barriers
+constexpr int OFF_K = OFF_Q + 2 * TILE16;      // KST stages x (K hi, K lo)   96 KB
+constexpr int OFF_V = OFF_K + KST * 2 * TILE16;  // V^T: VST stages x [2 key-chunks x (hi, lo) x 8 KB] = 96 KB
+constexpr int OFF_BAR = OFF_V + VST * 4 * TILE8; // barriers (P lives in tensor memory, in the columns of the S block it came from)
 constexpr int OFF_RED = OFF_BAR + 256;         // [2 halves][128 rows] floats: row max / row sum exchange
 constexpr int SMEM_BYTES = OFF_RED + 2 * 128 * 4 + 1024;
 
-enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11, B_PFULL = 13,
-       B_PEMPTY = 15, B_OFULL = 17, B_COUNT = 18 };
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = B_KFULL + KST, B_VFULL = B_KEMPTY + KST, B_VEMPTY = B_VFULL + VST,
+       B_SFULL = B_VEMPTY + VST, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2, B_OFULL = B_PFULL + 2, B_COUNT = B_OFULL + 1 };
 
 __global__ void __launch_bounds__(NT, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo,
@@ -152,11 +189,13 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
 
     if (warp == 0 && lane == 0) {
         mbar_init(bar + B_QFULL, 1);
+        for (int s = 0; s < KST; ++s) { mbar_init(bar + B_KFULL + s, 1); mbar_init(bar + B_KEMPTY + s, 1); }
+        for (int s = 0; s < VST; ++s) { mbar_init(bar + B_VFULL + s, 1); mbar_init(bar + B_VEMPTY + s, 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(bar + B_KFULL + s, 1); mbar_init(bar + B_KEMPTY + s, 1);
-            mbar_init(bar + B_SFULL + s, 1); mbar_init(bar + B_SEMPTY + s, 8);
-            mbar_init(bar + B_PFULL + s, 4); mbar_init(bar + B_PEMPTY + s, 1);
-            mbar_init(bar + B_VFULL + s, 1); mbar_init(bar + B_VEMPTY + s, 1);
+            // an S buffer is free again after 8 softmax-warp arrivals + 1 from the MMA warp: a plain arrive in pass 1, the
+            // commit of the P V product that read P out of the same columns in pass 2
+            mbar_init(bar + B_SFULL + s, 1); mbar_init(bar + B_SEMPTY + s, 9);
+            mbar_init(bar + B_PFULL + s, 4);
         }
         mbar_init(bar + B_OFULL, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -177,24 +216,28 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             tma_load_3d(smem + OFF_Q, &mQhi, bar + B_QFULL, 0, q0, bh);
             if (x3) tma_load_3d(smem + OFF_Q + TILE16, &mQlo, bar + B_QFULL, 0, q0, bh);
             for (int it = 0; it < 2 * nb; ++it) {          // K blocks: pass 1 then pass 2
-                const int j = it % nb, s = it & 1;
-                mbar_wait(bar + B_KEMPTY + s, ((it >> 1) & 1) ^ 1);
+                const int j = it % nb, s = it % KST;
+                mbar_wait(bar + B_KEMPTY + s, ((it / KST) & 1) ^ 1);
                 uint8_t* st = smem + OFF_K + s * 2 * TILE16;
                 const bool lo = x3 && it >= nb;             // pass 1 multiplies the hi parts only
                 mbar_expect_tx(bar + B_KFULL + s, lo ? kstage_bytes : (uint32_t)TILE16);
                 tma_load_3d(st, &mKhi, bar + B_KFULL + s, 0, j * KT, bh);
                 if (lo) tma_load_3d(st + TILE16, &mKlo, bar + B_KFULL + s, 0, j * KT, bh);
-                if (it >= nb) {                            // pass 2: the matching V^T block (two 64-key chunks), 2-stage ring
-                    const int vs = j & 1;
-                    mbar_wait(bar + B_VEMPTY + vs, ((j >> 1) & 1) ^ 1);
-                    mbar_expect_tx(bar + B_VFULL + vs, v_bytes);
-                    uint8_t* vt = smem + OFF_V + vs * 4 * TILE8;
-                    tma_load_3d(vt, &mVhi, bar + B_VFULL + vs, j * KT, 0, bh);
-                    tma_load_3d(vt + TILE8, &mVhi, bar + B_VFULL + vs, j * KT + 64, 0, bh);
-                    if (x3) {
-                        tma_load_3d(vt + 2 * TILE8, &mVlo, bar + B_VFULL + vs, j * KT, 0, bh);
-                        tma_load_3d(vt + 3 * TILE8, &mVlo, bar + B_VFULL + vs, j * KT + 64, 0, bh);
-                    }
+            }
+        }
+    } else if (warp == 10) {
+        // ===== TMA producer for V^T (pass 2 only; own warp so that a full K ring never delays it and vice versa) =====
+        if (elect_one()) {
+            for (int j = 0; j < nb; ++j) {                  // two 64-key chunks per block
+                const int vs = j % VST;
+                mbar_wait(bar + B_VEMPTY + vs, ((j / VST) & 1) ^ 1);
+                mbar_expect_tx(bar + B_VFULL + vs, v_bytes);
+                uint8_t* vt = smem + OFF_V + vs * 4 * TILE8;
+                tma_load_3d(vt, &mVhi, bar + B_VFULL + vs, j * KT, 0, bh);
+                tma_load_3d(vt + TILE8, &mVhi, bar + B_VFULL + vs, j * KT + 64, 0, bh);
+                if (x3) {
+                    tma_load_3d(vt + 2 * TILE8, &mVlo, bar + B_VFULL + vs, j * KT, 0, bh);
+                    tma_load_3d(vt + 3 * TILE8, &mVlo, bar + B_VFULL + vs, j * KT + 64, 0, bh);
                 }
             }
         }
@@ -205,12 +248,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
         mbar_wait(bar + B_QFULL, 0);
         tc_fence_after();
         auto issue_S = [&](int it, bool full) {   // S[it&1] = Q K^T for K ring slot it&1 (full: bf16x3, else hi x hi)
-            const int s = it & 1;
-            mbar_wait(bar + B_KFULL + s, (it >> 1) & 1);
+            const int s = it & 1, ks = it % KST;
+            mbar_wait(bar + B_KFULL + ks, (it / KST) & 1);
             mbar_wait(bar + B_SEMPTY + s, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t ka = smem_u32(smem + OFF_K + s * 2 * TILE16);
+                const uint32_t ka = smem_u32(smem + OFF_K + ks * 2 * TILE16);
                 const uint64_t dQh = make_smem_desc(qa), dQl = make_smem_desc(qa + TILE16);
                 const uint64_t dKh = make_smem_desc(ka), dKl = make_smem_desc(ka + TILE16);
                 const uint32_t td = tmem_base + s * 128;
@@ -218,13 +261,14 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
                 for (int k = 0; k < HD / 16; ++k) {
                     const uint64_t adv = (uint64_t)((k * 32) >> 4);
                     tc_mma(td, dQh + adv, dKh + adv, idS, k ? 1u : 0u);
-                    if (x3 && full) {
+                    if (x3 && full && !(p.dbg & 32)) {
                         tc_mma(td, dQh + adv, dKl + adv, idS, 1u);
                         tc_mma(td, dQl + adv, dKh + adv, idS, 1u);
                     }
                 }
-                tc_commit(bar + B_KEMPTY + s);
+                tc_commit(bar + B_KEMPTY + ks);
                 tc_commit(bar + B_SFULL + s);
+                if (!full) mbar_arrive(bar + B_SEMPTY + s);     // pass 1: nothing of ours reads this buffer later
             }
             __syncwarp();
         };
@@ -232,36 +276,37 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
         issue_S(nb, true);                                           // first S of pass 2
         for (int j = 0; j < nb; ++j) {
             if (j + 1 < nb) issue_S(nb + j + 1, true);               // overlap the next S with this block's softmax
-            const int vs = j & 1;
-            mbar_wait(bar + B_VFULL + vs, (j >> 1) & 1);
+            const int vs = j % VST;
+            mbar_wait(bar + B_VFULL + vs, (j / VST) & 1);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {                            // two 64-key halves, each its own pipeline stage
                 mbar_wait(bar + B_PFULL + c, j & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t pa = smem_u32(smem + OFF_P), va = smem_u32(smem + OFF_V + vs * 4 * TILE8);
+                    const uint32_t va = smem_u32(smem + OFF_V + vs * 4 * TILE8);
                     const uint32_t td = tmem_base + O_COL;
-                    const uint64_t dPh = make_smem_desc(pa + c * TILE16), dPl = make_smem_desc(pa + (2 + c) * TILE16);
+                    // P half c of this block sits in the S buffer's own columns: hi words [c*64, +32), lo words [c*64+32, +32)
+                    const uint32_t ph = tmem_base + ((nb + j) & 1) * 128 + c * 64, pl = ph + 32;
                     const uint64_t dVh = make_smem_desc(va + c * TILE8), dVl = make_smem_desc(va + (2 + c) * TILE8);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                        tc_mma(td, dPh + adv, dVh + adv, idO, (j | c | k) ? 1u : 0u);
-                        if (x3) {
-                            tc_mma(td, dPh + adv, dVl + adv, idO, 1u);
-                            tc_mma(td, dPl + adv, dVh + adv, idO, 1u);
+                        tc_mma_ts(td, ph + k * 8, dVh + adv, idO, (j | c | k) ? 1u : 0u);
+                        if (x3 && !(p.dbg & 16)) {
+                            tc_mma_ts(td, ph + k * 8, dVl + adv, idO, 1u);
+                            tc_mma_ts(td, pl + k * 8, dVh + adv, idO, 1u);
                         }
                     }
-                    tc_commit(bar + B_PEMPTY + c);
                     if (c == 1) {
                         tc_commit(bar + B_VEMPTY + vs);
+                        tc_commit(bar + B_SEMPTY + ((nb + j) & 1));     // S/P buffer reusable once these products retire
                         if (j == nb - 1) tc_commit(bar + B_OFULL);
                     }
                 }
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp < 10) {
         // ===== softmax / epilogue warps: thread == (query row, 64-key half) =====
         const int q = warp & 3;                    // TMEM lane quarter
         const int half = (warp - 2) >> 2;          // which 64 keys of every 128-key block (and which 32 columns of O)
@@ -279,9 +324,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_addr + s * 128 + half * 64 + g2 * 32, r);
                 const int kbase = it * KT + half * 64 + g2 * 32;
+                if (!(p.dbg & 8)) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (kbase + e < p.Nk) m = fmaxf(m, __uint_as_float(r[e]));
+                    for (int e = 0; e < 32; ++e)
+                        if (kbase + e < p.Nk) m = fmaxf(m, __uint_as_float(r[e]));
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -291,51 +338,47 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
         asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 softmax warps only
         m = fmaxf(m, red[(half ^ 1) * 128 + row]);
         asm volatile("bar.sync 1, 256;" ::: "memory");          // red[] is reused for the row sums below
-        // PASS 2: p = exp2((s - m) * scale*log2e) -> bf16 (hi, lo) written to swizzled smem; row sum
+        // PASS 2: p = exp2((s - m) * scale*log2e) -> packed bf16 (hi, lo) words stored back to tensor memory; row sum
         float l = 0.f;
         const float c1 = p.scale_log2e, c0 = -m * p.scale_log2e;
         for (int j = 0; j < nb; ++j) {
             const int it = nb + j, s = it & 1;
             mbar_wait(bar + B_SFULL + s, (it >> 1) & 1);
-            mbar_wait(bar + B_PEMPTY + half, (j & 1) ^ 1);     // the previous P V product has consumed this half's tiles
             tc_fence_after();
-            uint8_t* th = smem + OFF_P + half * TILE16 + row * 128;
-            uint8_t* tl = th + 2 * TILE16;
-#pragma unroll 1
-            for (int g2 = 0; g2 < 2; ++g2) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + lane_addr + s * 128 + half * 64 + g2 * 32, r);
-                const int kbase = j * KT + half * 64 + g2 * 32;
-                // only the last key block can hold padded keys: keep the masking out of the steady-state loop
-                const bool tail = kbase + 32 > p.Nk;
+            // all 64 scores of this half first: the P words overwrite the same columns
+            uint32_t r[64];
+            tmem_ld32_nowait(tmem_base + lane_addr + s * 128 + half * 64, r);
+            tmem_ld32_nowait(tmem_base + lane_addr + s * 128 + half * 64 + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int kbase = j * KT + half * 64;
+            const bool tail = kbase + 64 > p.Nk;        // only the last key block can hold padded keys
+            uint32_t hw[32], lw[32];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {                  // 8 keys = one 16 B chunk
-                    uint32_t hw[4], lw[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int k0 = g * 8 + 2 * e;
-                        float a = ex2_ftz(fmaf(__uint_as_float(r[k0]), c1, c0));
-                        float b = ex2_ftz(fmaf(__uint_as_float(r[k0 + 1]), c1, c0));
-                        if (tail) {
-                            if (kbase + k0 >= p.Nk) a = 0.f;
-                            if (kbase + k0 + 1 >= p.Nk) b = 0.f;
-                        }
-                        l += a + b;
-                        // packed split: one cvt.rn.bf16x2 for the hi pair, shift/mask to widen it back, one for the lo pair
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16),
-                                                                        b - __uint_as_float(hb & 0xffff0000u));
-                        hw[e] = hb;
-                        lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
-                    }
-                    const int chunk = (g2 * 4 + g) ^ (row & 7);            // SWIZZLE_128B: 16 B chunk index XOR (row % 8)
-                    *reinterpret_cast<uint4*>(th + chunk * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    if (x3) *reinterpret_cast<uint4*>(tl + chunk * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            for (int e = 0; e < 32; ++e) {
+                float a = fmaf(__uint_as_float(r[2 * e]), c1, c0);
+                float b = fmaf(__uint_as_float(r[2 * e + 1]), c1, c0);
+                if (!(p.dbg & 1)) { a = ex2_ftz(a); b = ex2_ftz(b); }
+                if (tail) {
+                    if (kbase + 2 * e >= p.Nk) a = 0.f;
+                    if (kbase + 2 * e + 1 >= p.Nk) b = 0.f;
+                }
+                l += a + b;
+                // packed split: one cvt.rn.bf16x2 for the hi pair, shift/mask to widen it back, one for the lo pair
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                hw[e] = hb;
+                lw[e] = 0;
+                if (!(p.dbg & 2)) {
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16), b - __uint_as_float(hb & 0xffff0000u));
+                    lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
             }
+            if (!(p.dbg & 4)) {
+                tmem_st32(tmem_base + lane_addr + s * 128 + half * 64, hw);
+                if (x3) tmem_st32(tmem_base + lane_addr + s * 128 + half * 64 + 32, lw);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
             tc_fence_before();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor-core (async) proxy
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar + B_SEMPTY + s); mbar_arrive(bar + B_PFULL + half); }
         }
@@ -438,6 +481,8 @@ ADB_API int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, cons
     p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.n_qtiles = adb_cdiv(Nq, QT);
     p.scale_log2e = scale * 1.4426950408889634f;
     p.Ohi = (__nv_bfloat16*)O_hi; p.Olo = (__nv_bfloat16*)O_lo; p.nterms = x3 ? 3 : 1;
+    static const int dbg = getenv("ADB_ATTN_DBG") ? atoi(getenv("ADB_ATTN_DBG")) : 0;
+    p.dbg = dbg;
     static bool attr = false;
     if (!attr) {
         ADB_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
