@@ -169,7 +169,8 @@ constexpr int OFF_RED = OFF_BAR + 256;         // [2 halves][128 rows] floats: r
 constexpr int SMEM_BYTES = OFF_RED + 2 * 128 * 4 + 1024;
 
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = B_KFULL + KST, B_VFULL = B_KEMPTY + KST, B_VEMPTY = B_VFULL + VST,
-       B_SFULL = B_VEMPTY + VST, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2, B_OFULL = B_PFULL + 2, B_COUNT = B_OFULL + 1 };
+       B_SFULL = B_VEMPTY + VST, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2 /*[S buffer][half]*/, B_OFULL = B_PFULL + 4,
+       B_COUNT = B_OFULL + 1 };
 
 __global__ void __launch_bounds__(NT, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo,
@@ -195,7 +196,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             // an S buffer is free again after 8 softmax-warp arrivals + 1 from the MMA warp: a plain arrive in pass 1, the
             // commit of the P V product that read P out of the same columns in pass 2
             mbar_init(bar + B_SFULL + s, 1); mbar_init(bar + B_SEMPTY + s, 9);
-            mbar_init(bar + B_PFULL + s, 4);
+            // one P-full barrier per (S buffer, half): a single barrier per half could advance two phases before the MMA warp
+            // looks (softmax of block j+1 only needs S_{j+1}, which is issued before P V of block j) and the parity wait would hang
+            mbar_init(bar + B_PFULL + 2 * s, 4); mbar_init(bar + B_PFULL + 2 * s + 1, 4);
         }
         mbar_init(bar + B_OFULL, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -280,7 +283,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             mbar_wait(bar + B_VFULL + vs, (j / VST) & 1);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {                            // two 64-key halves, each its own pipeline stage
-                mbar_wait(bar + B_PFULL + c, j & 1);
+                mbar_wait(bar + B_PFULL + 2 * ((nb + j) & 1) + c, (j >> 1) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t va = smem_u32(smem + OFF_V + vs * 4 * TILE8);
@@ -380,7 +383,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(bar + B_SEMPTY + s); mbar_arrive(bar + B_PFULL + half); }
+            if (lane == 0) { mbar_arrive(bar + B_SEMPTY + s); mbar_arrive(bar + B_PFULL + 2 * s + half); }
         }
         red[half * 128 + row] = l;
         asm volatile("bar.sync 1, 256;" ::: "memory");
