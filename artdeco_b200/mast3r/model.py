@@ -219,6 +219,9 @@ class AsymmetricMASt3R:
         B, _, H, W = image.shape
         if H % 16 or W % 16:
             raise AssertionError(f"Input image size ({H}x{W}) is not a multiple of patch size (16).")
+        if max(H, W) // 16 > ops.ROPE_TABLE_POSITIONS:
+            # the RoPE (cos, sin) table holds this many patch positions per axis; the kernels clamp beyond it, so refuse
+            raise ValueError(f"image side {max(H, W)} px exceeds the {ops.ROPE_TABLE_POSITIONS * 16} px the RoPE table covers")
         E = self.cfg["enc_embed_dim"]
         n = (H // 16) * (W // 16)
         with torch.cuda.device(image.device):

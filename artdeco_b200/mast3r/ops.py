@@ -92,6 +92,7 @@ def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-6, want_fp32=False, 
     return y, sp
 
 
+ROPE_TABLE_POSITIONS = 64      # patch positions per axis in the (cos, sin) table (1024 px at patch 16); n_pos default below
 _rope_tables: dict = {}
 
 
