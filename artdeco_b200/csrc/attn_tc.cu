@@ -426,6 +426,307 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constan
     }
 }
 
+// =====================================================================================================================
+// Variant 2 (opt-in, ADB_ATTN_KERNEL=2): TWO query tiles (256 queries) per CTA sharing every K / V^T block, in a PERSISTENT
+// CTA that loops over (batch*head, tile pair) work items.  Motivation (profiles/r01_attn_ablation.md): variant 1 is bound by
+// L2->SM traffic (80 KB of K/V per 128 queries per key block) and by a 5.7 us per-CTA fixed cost that nothing overlaps.
+// Here each K/V block serves 256 queries, and the epilogue of one item overlaps the first pass of the next.
+//   TMEM   S_a [0,128)  S_b [128,256)  O_a [256,320)  O_b [320,384): no second S buffer per tile -- the two tiles ping-pong
+//          (the MMA warp computes S_b while the softmax warps of tile a work, and so on); P overwrites S in place as above.
+//   warps  0: TMA Q + K   1: MMA   2..5: softmax/epilogue of tile a (thread == one query row, all 128 keys of a block,
+//          processed as two 64-key halves)   6..9: the same for tile b   10: TMA V^T
+//   hazards on S_x (written by the S MMA, read by softmax, overwritten by P, read by the P V MMA, overwritten by the next S):
+//          tcgen05.mma instructions execute in issue order, so issuing S_x(n+1) after P V_x(n) needs no barrier; the only
+//          handshakes are S-full (MMA -> softmax) and S-done (softmax -> MMA: scores read in pass 1 / P stored in pass 2).
+//   all barrier phases run on counters that continue across work items.
+// STATUS: compiled for sm_100a and reviewed, NOT YET RUN ON HARDWARE (the round's GPU budget was spent); therefore opt-in.
+// =====================================================================================================================
+constexpr int K2ST = 3, V2ST = 2;
+constexpr int OFF2_Q = 0;                                   // Q_a hi, Q_a lo, Q_b hi, Q_b lo        64 KB
+constexpr int OFF2_K = OFF2_Q + 4 * TILE16;                 // K2ST x (K hi, K lo)                   96 KB
+constexpr int OFF2_V = OFF2_K + K2ST * 2 * TILE16;          // V2ST x [2 chunks x (hi, lo) x 8 KB]   64 KB
+constexpr int OFF2_BAR = OFF2_V + V2ST * 4 * TILE8;
+constexpr int SMEM2_BYTES = OFF2_BAR + 256 + 1024;
+enum { C_QFULL = 0, C_QEMPTY = 1, C_KFULL = 2, C_KEMPTY = C_KFULL + K2ST, C_VFULL = C_KEMPTY + K2ST, C_VEMPTY = C_VFULL + V2ST,
+       C_SFULL = C_VEMPTY + V2ST, C_SDONE = C_SFULL + 2, C_OFULL = C_SDONE + 2, C_OEMPTY = C_OFULL + 2, C_COUNT = C_OEMPTY + 2 };
+
+__global__ void __launch_bounds__(NT, 1)
+attn_fused2_kernel(const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo,
+                   const __grid_constant__ CUtensorMap mKhi, const __grid_constant__ CUtensorMap mKlo,
+                   const __grid_constant__ CUtensorMap mVhi, const __grid_constant__ CUtensorMap mVlo,
+                   const AttnParams p, const int n_items, const int n_pairs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar = (uint64_t*)(smem + OFF2_BAR);
+    uint32_t* tmem_ptr = (uint32_t*)(bar + C_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool x3 = p.nterms == 3;
+    const int nb = (p.Nk + KT - 1) / KT;
+    const uint32_t q_bytes = (x3 ? 4 : 2) * TILE16, kstage_bytes = (x3 ? 2 : 1) * TILE16, v_bytes = (x3 ? 4 : 2) * TILE8;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(bar + C_QFULL, 1); mbar_init(bar + C_QEMPTY, 1);
+        for (int s = 0; s < K2ST; ++s) { mbar_init(bar + C_KFULL + s, 1); mbar_init(bar + C_KEMPTY + s, 1); }
+        for (int s = 0; s < V2ST; ++s) { mbar_init(bar + C_VFULL + s, 1); mbar_init(bar + C_VEMPTY + s, 1); }
+        for (int x = 0; x < 2; ++x) {
+            mbar_init(bar + C_SFULL + x, 1); mbar_init(bar + C_SDONE + x, 4);
+            mbar_init(bar + C_OFULL + x, 1); mbar_init(bar + C_OEMPTY + x, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer: Q pair once per item, K blocks for both passes =====
+        if (elect_one()) {
+            uint32_t kc = 0, wi = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++wi) {
+                const int bh = item / n_pairs, q0 = (item % n_pairs) * 2 * QT;
+                mbar_wait(bar + C_QEMPTY, (wi & 1) ^ 1);               // every S product of the previous item has retired
+                mbar_expect_tx(bar + C_QFULL, q_bytes);
+                tma_load_3d(smem + OFF2_Q, &mQhi, bar + C_QFULL, 0, q0, bh);
+                tma_load_3d(smem + OFF2_Q + 2 * TILE16, &mQhi, bar + C_QFULL, 0, q0 + QT, bh);
+                if (x3) {
+                    tma_load_3d(smem + OFF2_Q + TILE16, &mQlo, bar + C_QFULL, 0, q0, bh);
+                    tma_load_3d(smem + OFF2_Q + 3 * TILE16, &mQlo, bar + C_QFULL, 0, q0 + QT, bh);
+                }
+                for (int it = 0; it < 2 * nb; ++it, ++kc) {
+                    const int j = it % nb, s = kc % K2ST;
+                    mbar_wait(bar + C_KEMPTY + s, ((kc / K2ST) & 1) ^ 1);
+                    uint8_t* st = smem + OFF2_K + s * 2 * TILE16;
+                    const bool lo = x3 && it >= nb;
+                    mbar_expect_tx(bar + C_KFULL + s, lo ? kstage_bytes : (uint32_t)TILE16);
+                    tma_load_3d(st, &mKhi, bar + C_KFULL + s, 0, j * KT, bh);
+                    if (lo) tma_load_3d(st + TILE16, &mKlo, bar + C_KFULL + s, 0, j * KT, bh);
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===== TMA producer: V^T blocks (second pass only) =====
+        if (elect_one()) {
+            uint32_t vc = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int bh = item / n_pairs;
+                for (int j = 0; j < nb; ++j, ++vc) {
+                    const int vs = vc % V2ST;
+                    mbar_wait(bar + C_VEMPTY + vs, ((vc / V2ST) & 1) ^ 1);
+                    mbar_expect_tx(bar + C_VFULL + vs, v_bytes);
+                    uint8_t* vt = smem + OFF2_V + vs * 4 * TILE8;
+                    tma_load_3d(vt, &mVhi, bar + C_VFULL + vs, j * KT, 0, bh);
+                    tma_load_3d(vt + TILE8, &mVhi, bar + C_VFULL + vs, j * KT + 64, 0, bh);
+                    if (x3) {
+                        tma_load_3d(vt + 2 * TILE8, &mVlo, bar + C_VFULL + vs, j * KT, 0, bh);
+                        tma_load_3d(vt + 3 * TILE8, &mVlo, bar + C_VFULL + vs, j * KT + 64, 0, bh);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idS = make_idesc(128), idO = make_idesc(64);
+        const uint32_t qa = smem_u32(smem + OFF2_Q);
+        uint32_t kc = 0, vc = 0, wi = 0;
+        uint32_t sc[2] = {0u, 0u};            // S products issued so far per tile == index of the next S-full / S-done phase
+        // S_x(sc[x]) = Q_x K^T of the K stage `ks`; waits until the previous contents of S_x have been consumed
+        auto issue_S = [&](int x, int ks, bool full) {
+            if (sc[x] > 0) mbar_wait(bar + C_SDONE + x, (sc[x] - 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ka = smem_u32(smem + OFF2_K + ks * 2 * TILE16);
+                const uint64_t dQh = make_smem_desc(qa + x * 2 * TILE16), dQl = make_smem_desc(qa + x * 2 * TILE16 + TILE16);
+                const uint64_t dKh = make_smem_desc(ka), dKl = make_smem_desc(ka + TILE16);
+                const uint32_t td = tmem_base + x * 128;
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                    tc_mma(td, dQh + adv, dKh + adv, idS, k ? 1u : 0u);
+                    if (x3 && full) {
+                        tc_mma(td, dQh + adv, dKl + adv, idS, 1u);
+                        tc_mma(td, dQl + adv, dKh + adv, idS, 1u);
+                    }
+                }
+                tc_commit(bar + C_SFULL + x);
+            }
+            __syncwarp();
+            ++sc[x];
+        };
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++wi) {
+            mbar_wait(bar + C_QFULL, wi & 1);
+            // ---- pass 1: hi x hi scores for the row maxima ----
+            for (int it = 0; it < nb; ++it, ++kc) {
+                const int ks = kc % K2ST;
+                mbar_wait(bar + C_KFULL + ks, (kc / K2ST) & 1);
+                issue_S(0, ks, false);
+                issue_S(1, ks, false);
+                if (elect_one()) tc_commit(bar + C_KEMPTY + ks);
+                __syncwarp();
+            }
+            // ---- pass 2: S in bf16x3, P V; software-pipelined so that S_x(j+1) is queued right behind P V_x(j) ----
+            {
+                const int ks = kc % K2ST;
+                mbar_wait(bar + C_KFULL + ks, (kc / K2ST) & 1);
+                issue_S(0, ks, true);
+                issue_S(1, ks, true);
+                if (elect_one()) tc_commit(bar + C_KEMPTY + ks);
+                __syncwarp();
+                ++kc;
+            }
+            for (int j = 0; j < nb; ++j, ++vc) {
+                const int vs = vc % V2ST;
+                mbar_wait(bar + C_VFULL + vs, (vc / V2ST) & 1);
+                const bool more = j + 1 < nb;
+                const int ks = kc % K2ST;
+                if (more) mbar_wait(bar + C_KFULL + ks, (kc / K2ST) & 1);
+#pragma unroll 1
+                for (int x = 0; x < 2; ++x) {
+                    mbar_wait(bar + C_SDONE + x, (sc[x] - 1) & 1);                       // P_x(j) is in tensor memory
+                    if (j == 0) mbar_wait(bar + C_OEMPTY + x, (wi & 1) ^ 1);               // previous item's O_x has been read out
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t va = smem_u32(smem + OFF2_V + vs * 4 * TILE8);
+                        const uint32_t td = tmem_base + O_COL + x * 64;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const uint32_t ph = tmem_base + x * 128 + c * 64, pl = ph + 32;
+                            const uint64_t dVh = make_smem_desc(va + c * TILE8), dVl = make_smem_desc(va + (2 + c) * TILE8);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                                tc_mma_ts(td, ph + k * 8, dVh + adv, idO, (j | c | k) ? 1u : 0u);
+                                if (x3) {
+                                    tc_mma_ts(td, ph + k * 8, dVl + adv, idO, 1u);
+                                    tc_mma_ts(td, pl + k * 8, dVh + adv, idO, 1u);
+                                }
+                            }
+                        }
+                        if (x == 1) tc_commit(bar + C_VEMPTY + vs);
+                        if (!more) tc_commit(bar + C_OFULL + x);
+                    }
+                    __syncwarp();
+                    if (more) issue_S(x, ks, true);            // in-order tensor pipe: runs after the P V_x(j) just queued
+                }
+                if (more) {
+                    if (elect_one()) tc_commit(bar + C_KEMPTY + ks);
+                    __syncwarp();
+                    ++kc;
+                } else {
+                    if (elect_one()) tc_commit(bar + C_QEMPTY);   // the last S products of this item are queued: Q may be replaced
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ===== softmax / epilogue warps: tile x, thread == query row =====
+        const int x = (warp - 2) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t s_addr = tmem_base + ((uint32_t)(q * 32) << 16) + x * 128;
+        const uint32_t o_addr = tmem_base + ((uint32_t)(q * 32) << 16) + O_COL + x * 64;
+        uint32_t n = 0, wi = 0;                 // n: S_x products consumed so far (== phase index of S-full / S-done)
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++wi) {
+            const int bh = item / n_pairs, q0 = (item % n_pairs) * 2 * QT + x * QT;
+            float m = -3.0e38f;
+            for (int it = 0; it < nb; ++it, ++n) {
+                mbar_wait(bar + C_SFULL + x, n & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(s_addr + c * 32, r);
+                    const int kbase = it * KT + c * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (kbase + e < p.Nk) m = fmaxf(m, __uint_as_float(r[e]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + C_SDONE + x);
+            }
+            float l = 0.f;
+            const float c1 = p.scale_log2e, c0 = -m * p.scale_log2e;
+            for (int j = 0; j < nb; ++j, ++n) {
+                mbar_wait(bar + C_SFULL + x, n & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    // the P words of this half land in the columns its own scores came from; the other half is untouched
+                    uint32_t r[64];
+                    tmem_ld32_nowait(s_addr + half * 64, r);
+                    tmem_ld32_nowait(s_addr + half * 64 + 32, r + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int kbase = j * KT + half * 64;
+                    const bool tail = kbase + 64 > p.Nk;
+                    uint32_t hw[32], lw[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        float a = ex2_ftz(fmaf(__uint_as_float(r[2 * e]), c1, c0));
+                        float b = ex2_ftz(fmaf(__uint_as_float(r[2 * e + 1]), c1, c0));
+                        if (tail) {
+                            if (kbase + 2 * e >= p.Nk) a = 0.f;
+                            if (kbase + 2 * e + 1 >= p.Nk) b = 0.f;
+                        }
+                        l += a + b;
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16), b - __uint_as_float(hb & 0xffff0000u));
+                        hw[e] = hb;
+                        lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    tmem_st32(s_addr + half * 64, hw);
+                    if (x3) tmem_st32(s_addr + half * 64 + 32, lw);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + C_SDONE + x);
+            }
+            // epilogue: O_x / l -> bf16 split in [B, Nq, heads*64]; overlaps the first pass of the next item
+            mbar_wait(bar + C_OFULL + x, wi & 1);
+            tc_fence_after();
+            const float inv = 1.0f / l;
+            const int qrow = q0 + row;
+            const int b = bh / p.heads, hh = bh % p.heads;
+            const size_t o = ((size_t)b * p.Nq + qrow) * (size_t)(p.heads * HD) + (size_t)hh * HD;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld32(o_addr + c * 32, r);
+                if (qrow < p.Nq) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a = __uint_as_float(r[g * 8 + 2 * e]) * inv, bb = __uint_as_float(r[g * 8 + 2 * e + 1]) * inv;
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+                            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hb << 16), bb - __uint_as_float(hb & 0xffff0000u));
+                            hw[e] = hb;
+                            lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        *reinterpret_cast<uint4*>(p.Ohi + o + c * 32 + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        if (p.Olo) *reinterpret_cast<uint4*>(p.Olo + o + c * 32 + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar + C_OEMPTY + x);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -490,6 +791,26 @@ ADB_API int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, cons
     if (!attr) {
         ADB_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
+    }
+    static const int variant = getenv("ADB_ATTN_KERNEL") ? atoi(getenv("ADB_ATTN_KERNEL")) : 1;
+    if (variant == 2) {
+        // two query tiles per persistent CTA (see attn_fused2_kernel): opt-in until it has been validated on hardware
+        static bool attr2 = false;
+        static int num_sms = 0;
+        if (!attr2) {
+            int dev = 0;
+            ADB_CUDA(cudaGetDevice(&dev));
+            ADB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+            ADB_CUDA(cudaFuncSetAttribute(attn_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+            attr2 = true;
+        }
+        const int n_pairs = adb_cdiv(Nq, 2 * QT);
+        const long long items = bh * n_pairs;
+        ADB_REQUIRE(items < 2147483647LL, "adb_attention_bf16: too many work items");
+        const int grid2 = (int)(items < num_sms ? items : num_sms);
+        attn_fused2_kernel<<<grid2, NT, SMEM2_BYTES, stream>>>(mQh, mQl, mKh, mKl, mVh, mVl, p, (int)items, n_pairs);
+        ADB_CHECK_LAUNCH("attn_fused2_kernel");
+        return ADB_OK;
     }
     const long long grid = bh * p.n_qtiles;
     attn_fused_kernel<<<(unsigned)grid, NT, SMEM_BYTES, stream>>>(mQh, mQl, mKh, mKl, mVh, mVl, p);
