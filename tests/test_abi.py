@@ -54,3 +54,20 @@ def test_no_cpu_fallback_without_gpu():
     from artdeco_b200.ssim import fused_ssim
     with pytest.raises(_lib.ArtdecoB200Error):
         fused_ssim(torch.rand(1, 3, 32, 32), torch.rand(1, 3, 32, 32))
+
+
+def test_header_is_plain_c_and_cpp(tmp_path):
+    """The boundary is a C ABI: include/artdeco_b200.h must compile as C99 and as C++17 with no CUDA or torch headers."""
+    import shutil
+    inc = ROOT / "include"
+    for comp, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "cpp")):
+        exe = shutil.which(comp, path="/usr/bin:/bin") or shutil.which(comp)
+        if exe is None:
+            continue
+        src = tmp_path / f"hdr.{ext}"
+        src.write_text('#include "artdeco_b200.h"\nint main(void) { return 0; }\n')
+        r = subprocess.run([exe, std, "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", f"-I{inc}", str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    text = (inc / "artdeco_b200.h").read_text()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S).lower() and "#include <cuda" not in text
