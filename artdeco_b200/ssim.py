@@ -6,7 +6,6 @@ and return conventions; the compute goes through the C ABI (``adb_ssim_forward/b
 """
 from __future__ import annotations
 
-
 import torch
 
 from . import _lib

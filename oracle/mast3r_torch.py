@@ -13,7 +13,6 @@ same deterministic weights into it and checks this file agrees (max rel err < 1e
 that travel to the GPU box (the reference has no tests or vectors of its own for this path)."""
 from __future__ import annotations
 
-
 import torch
 import torch.nn.functional as F
 
