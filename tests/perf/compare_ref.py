@@ -5,7 +5,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from artdeco_b200 import synthetic  # noqa: E402
 from artdeco_b200.knn import distCUDA2, distIndex2  # noqa: E402

@@ -4,7 +4,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from artdeco_b200.mast3r import FULL_CFG, AsymmetricMASt3R  # noqa: E402
 from oracle import mast3r_torch as mt  # noqa: E402
 from tools.prof_mast3r import random_state  # noqa: E402

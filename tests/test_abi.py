@@ -40,9 +40,20 @@ def test_product_path_never_imports_oracle():
     for py in (ROOT / "artdeco_b200").rglob("*.py"):
         src = py.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{py} imports the oracle"
-    for py in (ROOT / "shims").rglob("*.py"):
+    for py in list((ROOT / "shims").rglob("*.py")) + list((ROOT / "tools").rglob("*.py")):
         src = py.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{py} imports the oracle"
+    # the two sanctioned users outside tests/: smoke() and the bench's CPU legs -- and only inside those functions
+    import ast
+    allowed = {"__graft_entry__.py": {"build", "smoke", "_smoke_mast3r"}, "bench.py": {"cpu_oracle_leg", "bench_mast3r"}}
+    for name, funcs in allowed.items():
+        tree = ast.parse((ROOT / name).read_text())
+        for node in tree.body:
+            inner = [n for n in ast.walk(node) if isinstance(n, (ast.Import, ast.ImportFrom))]
+            for imp in inner:
+                mods = [a.name for a in imp.names] if isinstance(imp, ast.Import) else [imp.module or ""]
+                if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                    assert isinstance(node, ast.FunctionDef) and node.name in funcs, f"{name}: oracle imported outside {funcs}"
 
 
 def test_no_cpu_fallback_without_gpu():
