@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE: an executable model of the synchronisation protocols of the two fused-attention kernels
+"""TEST INFRASTRUCTURE: an executable model of the synchronisation protocols of the two fused-attention kernels and the GEMM
 (artdeco_b200/csrc/attn_tc.cu), explored under random interleavings on the CPU.
 
 Why: the kernels are warp-specialised pipelines glued together by mbarriers whose waits see only the PARITY of a phase.
@@ -449,4 +449,83 @@ def variant2(nb, n_items, seed, kst=3, vst=2):
     M.agents = {"tma_k": producer_k(), "tma_v": producer_v(), "mma": mma()}
     for w in range(8):
         M.agents[f"softmax{w}"] = softmax(w >> 2)()
+    return M
+
+
+# =====================================================================================================================
+# The persistent tcgen05 GEMM (artdeco_b200/csrc/gemm_tc.cu): TMA ring + double-buffered TMEM accumulator per (tile, K-chunk)
+# =====================================================================================================================
+def gemm(n_tiles, num_kb, seed, stages=3, kchunk=8):
+    M = Machine(seed)
+    for s in range(stages):
+        M.bar(f"full{s}", 1); M.bar(f"empty{s}", 1)
+    for b in range(2):
+        M.bar(f"tmem_full{b}", 1); M.bar(f"tmem_empty{b}", 8)
+    stage = [None] * stages
+    acc = [dict(unit=None, kbs=0, reads=8) for _ in range(2)]        # unit = (tile, chunk index)
+    chunks = [(kb0, min(kb0 + kchunk, num_kb)) for kb0 in range(0, num_kb, kchunk)]
+
+    def loaded(s, it):
+        def f():
+            if stage[s] is not None:
+                raise Hazard(f"smem stage {s} overwritten while holding k-block load {stage[s]}")
+            stage[s] = it
+        return f
+
+    def producer():
+        it = 0
+        for _ in range(n_tiles):
+            for _ in range(num_kb):
+                s = it % stages
+                yield M.wait(f"empty{s}", ((it // stages) & 1) ^ 1)
+                M.loads.append((loaded(s, it), f"full{s}"))
+                it += 1
+
+    def mma_kb(s, it, buf, unit, first):
+        def f():
+            if stage[s] != it:
+                raise Hazard(f"MMA expected k-block load {it} in stage {s}, found {stage[s]}")
+            a = acc[buf]
+            if first:
+                if a["reads"] < 8:
+                    raise Hazard(f"accumulator {buf} re-initialised before the epilogue drained {a['unit']}")
+                acc[buf] = a = dict(unit=unit, kbs=0, reads=0)
+            elif a["unit"] != unit:
+                raise Hazard("accumulate into a buffer owned by another (tile, chunk)")
+            a["kbs"] += 1
+            stage[s] = None
+        return f
+
+    def mma():
+        it = lc = 0
+        for tile in range(n_tiles):
+            for ci, (kb0, kb1) in enumerate(chunks):
+                buf = lc & 1
+                yield M.wait(f"tmem_empty{buf}", ((lc >> 1) & 1) ^ 1)
+                for kb in range(kb0, kb1):
+                    s = it % stages
+                    yield M.wait(f"full{s}", (it // stages) & 1)
+                    M.pipe.append(("mma", mma_kb(s, it, buf, (tile, ci), kb == kb0)))
+                    M.pipe.append(("commit", f"empty{s}"))
+                    if kb == kb1 - 1:
+                        M.pipe.append(("commit", f"tmem_full{buf}"))
+                    it += 1
+                lc += 1
+
+    def epilogue():
+        lc = 0
+        for tile in range(n_tiles):
+            for ci, (kb0, kb1) in enumerate(chunks):
+                buf = lc & 1
+                yield M.wait(f"tmem_full{buf}", (lc >> 1) & 1)
+                a = acc[buf]
+                if a["unit"] != (tile, ci) or a["kbs"] != kb1 - kb0:
+                    raise Hazard(f"epilogue of {(tile, ci)} read accumulator of {a['unit']} with {a['kbs']} k-blocks")
+                a["reads"] += 1
+                M.bars[f"tmem_empty{buf}"].arrive()
+                lc += 1
+
+    M.agents = {"tma": producer(), "mma": mma()}
+    for w in range(8):
+        M.agents[f"epi{w}"] = epilogue()
     return M

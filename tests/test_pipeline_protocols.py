@@ -1,9 +1,9 @@
-"""Random-interleaving exploration of the fused-attention kernels' mbarrier protocols (tests/attn_protocol_model.py).
+"""Random-interleaving exploration of the fused-attention kernels' mbarrier protocols (tests/pipeline_protocol_model.py).
 CPU only.  The shipped protocols must run to completion with every data-hazard check silent under thousands of schedules;
 the protocol of the first tensor-memory-P version (one P-full barrier per half) must be caught."""
 import pytest
 
-from attn_protocol_model import Hazard, variant1, variant2
+from pipeline_protocol_model import Hazard, variant1, variant2
 
 
 @pytest.mark.parametrize("nb", [1, 2, 3, 4, 8])
@@ -46,7 +46,7 @@ def _mutant(old, new, which, args, seeds=120):
     """Runs the model with one line of its source replaced; returns how many schedules raised a Hazard."""
     import inspect
 
-    import attn_protocol_model as m
+    import pipeline_protocol_model as m
     src = inspect.getsource(m)
     assert old in src
     ns = {}
@@ -75,3 +75,11 @@ def _mutant(old, new, which, args, seeds=120):
 ])
 def test_model_is_sensitive_to_protocol_mutations(label, old, new, which, args):
     assert _mutant(old, new, which, args) > 0, label
+
+
+@pytest.mark.parametrize("n_tiles,num_kb,stages", [(1, 1, 3), (3, 16, 3), (4, 9, 6), (2, 20, 3), (5, 3, 2)])
+def test_gemm_pipeline_protocol(n_tiles, num_kb, stages):
+    """gemm_tc_kernel: TMA ring, K-chunk promotion through the two TMEM accumulators, 8 epilogue warps."""
+    from pipeline_protocol_model import gemm
+    for seed in range(150):
+        gemm(n_tiles, num_kb, seed, stages=stages).run()
