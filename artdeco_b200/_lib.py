@@ -78,7 +78,7 @@ LAUNCHES = {
     "adb_raster_isect_emit": 1, "adb_raster_sort": 8, "adb_raster_tile_offsets": 1, "adb_raster_blend_fwd": 1,
     "adb_raster_blend_bwd": 1, "adb_raster_project_bwd": 1,
     "adb_raster_project_fwd_legacy": 1, "adb_raster_isect_emit_legacy": 1, "adb_raster_blend_fwd_legacy": 1,
-    "adb_raster_blend_bwd_legacy": 1,
+    "adb_raster_blend_bwd_legacy": 1, "adb_raster_tile_count_scan": 2, "adb_raster_tile_scatter_sort": 2,
 }
 
 

@@ -30,6 +30,7 @@
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
 
 namespace {
 
@@ -761,6 +762,14 @@ int make_map(CUtensorMap* map, const void* ptr, long long batch, int rows, int c
 // O[b, n, h*64 + d] = sum_k softmax_k(scale * <Q[b,h,n,:], K[b,h,k,:]>) * V[b,h,k,d]   (head_dim 64)
 //   Q: bf16 split [B*heads, Nq, 64];  K: [B*heads, Nk, 64];  Vt: [B*heads, 64, Nkpad] (Nkpad % 8 == 0, zero padded);
 //   O: bf16 split [B, Nq, heads*64].  *_lo all non-NULL selects bf16x3.
+// 0 = automatic (default; env ADB_ATTN_KERNEL overrides at load), 1 = one query tile per CTA, 2 = two query tiles per
+// persistent CTA.  Returns the previous setting.  Both variants produce the same values to rounding (tests/test_gemm.py).
+static std::atomic<int> g_attn_variant{getenv("ADB_ATTN_KERNEL") ? atoi(getenv("ADB_ATTN_KERNEL")) : 0};
+ADB_API int adb_attention_set_variant(int variant) {
+    if (variant < 0 || variant > 2) return -1;
+    return g_attn_variant.exchange(variant);
+}
+
 ADB_API int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, const void* Q_hi, const void* Q_lo,
                                const void* K_hi, const void* K_lo, const void* Vt_hi, const void* Vt_lo, float scale,
                                void* O_hi, void* O_lo, cudaStream_t stream) {
@@ -787,23 +796,26 @@ ADB_API int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, cons
     p.Ohi = (__nv_bfloat16*)O_hi; p.Olo = (__nv_bfloat16*)O_lo; p.nterms = x3 ? 3 : 1;
     static const int dbg = getenv("ADB_ATTN_DBG") ? atoi(getenv("ADB_ATTN_DBG")) : 0;
     p.dbg = dbg;
-    static bool attr = false;
-    if (!attr) {
-        ADB_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr = true;
-    }
-    static const int variant = getenv("ADB_ATTN_KERNEL") ? atoi(getenv("ADB_ATTN_KERNEL")) : 1;
-    if (variant == 2) {
-        // two query tiles per persistent CTA (see attn_fused2_kernel): opt-in until it has been validated on hardware
-        static bool attr2 = false;
-        static int num_sms = 0;
-        if (!attr2) {
-            int dev = 0;
-            ADB_CUDA(cudaGetDevice(&dev));
-            ADB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    static AdbDeviceOnce once;
+    int num_sms = 0;
+    {
+        const int rc = once.ensure([]() -> int {
+            ADB_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             ADB_CUDA(cudaFuncSetAttribute(attn_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-            attr2 = true;
-        }
+            return ADB_OK;
+        }, &num_sms);
+        if (rc != ADB_OK) return rc;
+    }
+    // Kernel choice.  Variant 2 (two query tiles per persistent CTA) halves the K/V stream per query but its work items are
+    // twice as long, so it wins when its item count quantises well onto the SMs.  Measured on B200 (tools/bench_attn.py,
+    // profiles/r02_attention_variants.md): one variant-2 item costs ~1.75x a variant-1 CTA; pick the smaller wave count.
+    int variant = g_attn_variant.load(std::memory_order_relaxed);
+    if (variant == 0) {
+        const long long n1 = bh * p.n_qtiles, n2 = bh * adb_cdiv(Nq, 2 * QT);
+        const long long w1 = (n1 + num_sms - 1) / num_sms, w2 = (n2 + num_sms - 1) / num_sms;
+        variant = (10 * w1 >= 17 * w2) ? 2 : 1;
+    }
+    if (variant == 2) {
         const int n_pairs = adb_cdiv(Nq, 2 * QT);
         const long long items = bh * n_pairs;
         ADB_REQUIRE(items < 2147483647LL, "adb_attention_bf16: too many work items");

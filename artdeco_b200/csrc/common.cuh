@@ -31,6 +31,35 @@ void adb_set_error_msg(const char* msg);
 
 static inline int adb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+#ifdef __cplusplus
+#include <mutex>
+// One-time, PER-DEVICE launch setup (cudaFuncSetAttribute is a per-device property and the SM count differs between
+// devices: a process may drive several GPUs, as the reference allows with --device_mapper / device_backend).
+// Keyed by the current device ordinal; the mutex makes the first call on each device thread-safe.
+struct AdbDeviceOnce {
+    static constexpr int MAX_DEV = 64;
+    std::mutex mu;
+    bool done[MAX_DEV] = {};
+    int sms[MAX_DEV] = {};
+    // Runs `setup()` (returns an ADB status) the first time the CURRENT device is seen; *num_sms = its SM count.
+    template <class F>
+    int ensure(F&& setup, int* num_sms = nullptr) {
+        int dev = 0;
+        ADB_CUDA(cudaGetDevice(&dev));
+        ADB_REQUIRE(dev >= 0 && dev < MAX_DEV, "device ordinal out of range");
+        std::lock_guard<std::mutex> lk(mu);
+        if (!done[dev]) {
+            ADB_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+            const int rc = setup();
+            if (rc != ADB_OK) return rc;
+            done[dev] = true;
+        }
+        if (num_sms) *num_sms = sms[dev];
+        return ADB_OK;
+    }
+};
+#endif
+
 __device__ __forceinline__ float adb_warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     v += __shfl_xor_sync(0xffffffffu, v, 8);

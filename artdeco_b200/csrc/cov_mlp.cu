@@ -229,13 +229,21 @@ ADB_API int adb_cov_mlp_backward(long long N, int Fg, int Fl, const float* globa
     const int blocks = adb_cdiv(N, TPB);
     const size_t smem = sizeof(float) * ((size_t)D * D + D + 7 * D + 8 + 3 * (size_t)TPB * (D + 1) + (size_t)TPB * 8);
     if (D == 32) {
-        static bool attr = false;
-        if (!attr) { ADB_CUDA(cudaFuncSetAttribute(cov_mlp_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        static AdbDeviceOnce once;
+        const int rc = once.ensure([smem]() -> int {
+            ADB_CUDA(cudaFuncSetAttribute(cov_mlp_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            return ADB_OK;
+        });
+        if (rc != ADB_OK) return rc;
         cov_mlp_bwd_kernel<32><<<blocks, TPB, smem, stream>>>(N, m, global_feat, local_feat, cls_id, scaling, rotation, v_scale_out,
                                                              v_rot_out, v_scaling, v_rotation, v_local_feat, v_global_feat, v_W1, v_b1, v_W2, v_b2);
     } else {
-        static bool attr = false;
-        if (!attr) { ADB_CUDA(cudaFuncSetAttribute(cov_mlp_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        static AdbDeviceOnce once;
+        const int rc = once.ensure([smem]() -> int {
+            ADB_CUDA(cudaFuncSetAttribute(cov_mlp_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            return ADB_OK;
+        });
+        if (rc != ADB_OK) return rc;
         cov_mlp_bwd_kernel<64><<<blocks, TPB, smem, stream>>>(N, m, global_feat, local_feat, cls_id, scaling, rotation, v_scale_out,
                                                              v_rot_out, v_scaling, v_rotation, v_local_feat, v_global_feat, v_W1, v_b1, v_W2, v_b2);
     }

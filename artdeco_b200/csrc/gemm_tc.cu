@@ -512,13 +512,15 @@ int launch(const CUtensorMap& mAhi, const CUtensorMap& mAlo, const CUtensorMap& 
            GemmParams& p, long long num_tiles, cudaStream_t stream) {
     p.stages = p.nterms == 3 ? 3 : 6;
     const size_t smem = (size_t)p.stages * (p.nterms == 3 ? 4 : 2) * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        ADB_CUDA(cudaGetDevice(&dev));
-        ADB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        ADB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        ADB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    static AdbDeviceOnce once;
+    int num_sms = 0;
+    {
+        const int rc = once.ensure([]() -> int {
+            ADB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            ADB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            return ADB_OK;
+        }, &num_sms);
+        if (rc != ADB_OK) return rc;
     }
     const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
     if (p.rope_ndst > 0) gemm_tc_kernel<true><<<grid, NTHREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, p);

@@ -5,31 +5,50 @@
 //   pixel centre (j+0.5, i+0.5); sigma = .5(a dx^2 + c dy^2) + b dx dy; alpha = min(.999, o exp(-sigma));
 //   skip if sigma<0 or alpha<1/255; stop when T(1-alpha) <= 1e-4; out += feat*alpha*T; alpha_out = 1-T.
 //
-// B200-first structure (one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block):
-//  * the tile's slice of the depth-sorted list is staged in shared memory 256 splats at a time, each thread
-//    gathering one 48 B record with 3 coalesced-in-record LDG.128;
-//  * WARP-COOPERATIVE CULLING: lane l tests splat l of a 32-chunk against the warp's 8x4 block with the
-//    splat's own integer radii (outside them alpha < 1/255 by construction of the radius), a ballot gives
-//    the warp its private hit list, and only those splats are evaluated (LDS.128 broadcast reads);
-//  * a lane evaluates exp() only when sigma <= ln(255*opacity)+margin (stored in the record), i.e. only when
-//    alpha can reach 1/255 — the exact alpha test still runs inside, so results equal the plain algorithm;
-//  * backward: per-splat gradients (10 values) are reduced over the warp with a packed 12-shuffle
-//    butterfly (instead of 10 x 5), combined across the 8 warps with one shared-memory RED per value, and
-//    flushed with three 128-bit vector REDs per (tile, splat) (red.global.add.v4.f32; gsplat issues 10
-//    scalar atomics per WARP).
+// Both kernels are INSTRUCTION-ISSUE bound on this workload (one 48 B record is reused by up to 256 pixels; DRAM
+// utilisation is ~2 %), so the design minimises issued instructions per (warp, splat) evaluation:
+//  * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block (the 32-lane shape with the best lane occupancy
+//    on small splats: 51 % of the lanes of an evaluated (warp, splat) pair contribute at the BASELINE workload);
+//  * the tile's slice of the depth-sorted list is staged 256 splats at a time as 48 B shared-memory records, the conic
+//    pre-scaled by log2(e)/2 so that sigma is 5 FP32 ops and alpha is one MUFU.EX2 without a range-reduction multiply;
+//  * WARP-COOPERATIVE CULLING: lane l tests splat l of a 32-chunk against the warp's block (integer radius box, then the
+//    exact minimum of sigma over the block's rectangle against ln(255 o)); a ballot compacts the survivors into the
+//    warp's private 16-bit hit list, padded to a multiple of four with a never-visible dummy record so the evaluation
+//    loop is unrolled by four with one LDS.64 of list entries and no remainder code;
+//  * the evaluation bodies are branch-free (predicated selects), so the four unrolled bodies interleave;
+//  * BACKWARD — the per-splat reduction over the warp's 32 pixels is NOT a shuffle butterfly.  All ten per-Gaussian
+//    sums are dot products of two per-(pixel,splat) scalars with weights that do not depend on the splat:
+//        raw moments  sum_p vs(p) * {1, lx, ly, lx^2, lx ly, ly^2}   (vs = dL/dsigma, lx/ly = pixel offset in the block)
+//        feature grads sum_p fac(p) * v_out[p][0..3]                  (fac = alpha*T)
+//    i.e. a [slots x 32 pixels] x [32 x 10] product.  A lane therefore stores just (vs, fac) per evaluation (one STS.64)
+//    into a per-warp slot buffer; every S evaluations the warp transposes roles (lane = slot), streams the slot's row
+//    with LDS.128, applies the lane-constant integer weights as immediates (row sums first: 7.75 FMA per pixel
+//    instead of 10) and converts the block-origin moments to splat-centred ones once per (warp, splat):
+//        sum vs dx = ex S0 - Sx,  sum vs dx^2 = ex (ex S0 - 2 Sx) + Sxx, ...   (ex = mean_x - block origin)
+//    About 11 issued instructions per evaluation against ~55 for the packed butterfly + shared atomics it replaces, and
+//    the nine moment/feature multiplies leave the per-pixel body as well;
+//  * results leave with three 128/64-bit vector REDs per (warp, splat) (red.global.add.v4.f32).
 #include "raster_common.cuh"
 #include <stdlib.h>
 
 namespace {
 
 constexpr int BLOCK = ADB_TILE * ADB_TILE;  // 256
+constexpr int NWARP = BLOCK / 32;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int DUMMY = BLOCK;                // index of the never-visible padding record
+constexpr int LIST_STRIDE = BLOCK + 8;      // u16 entries per warp (padding to a multiple of 4 fits)
+constexpr float LOG2E = 1.4426950408889634f;
 
-__device__ __forceinline__ void gather_splat(const float* __restrict__ splats, int g, float4& A, float4& B, float4& C) {
-    const float4* p = reinterpret_cast<const float4*>(splats + (size_t)g * ADB_SPLAT_STRIDE);
-    A = __ldg(p);
-    B = __ldg(p + 1);
-    C = __ldg(p + 2);
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // warp block geometry: warp w covers pixels x in [bx*16 + (w&1)*8, +8), y in [by*16 + (w>>1)*4, +4)
@@ -37,69 +56,105 @@ struct WarpRect {
     float xlo, xhi, ylo, yhi;  // pixel-centre range
 };
 
-// Can splat (A,B) reach alpha >= 1/255 anywhere in the warp's block?  Two conservative tests:
+// Shared-memory record (3 x float4, 48 B stride: conflict-free for both the staging stores and the broadcast loads):
+//   A = (mx, my, ha, b2)   B = (hc, opacity, smax2, bits rx|ry<<16)   C = (r, g, b, depth | 1/depth for LEGACY)
+// with ha = log2e * a/2, b2 = log2e * b, hc = log2e * c/2, smax2 = log2e * (ln(255 o) + margin):
+//   sigma2 = log2e * sigma = dx (ha dx + b2 dy) + hc dy^2,   alpha = o * 2^(-sigma2).
+template <bool LEGACY>
+__device__ __forceinline__ void stage_record(float4* __restrict__ rec, const float* __restrict__ splats, int g) {
+    const float4* p = reinterpret_cast<const float4*>(splats + (size_t)g * ADB_SPLAT_STRIDE);
+    float4 A = __ldg(p), B = __ldg(p + 1), C = __ldg(p + 2);
+    A.z *= 0.5f * LOG2E;
+    A.w *= LOG2E;
+    B.x *= 0.5f * LOG2E;
+    B.z *= LOG2E;
+    if (LEGACY) C.w = 1.0f / C.w;   // Inria: 4th channel blends 1/z (v_splats slot 9 is then dL/d(1/z))
+    rec[0] = A;
+    rec[1] = B;
+    rec[2] = C;
+}
+
+__device__ __forceinline__ void write_dummy(float4* __restrict__ rec) {
+    rec[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec[1] = make_float4(0.f, 0.f, -1.0f, 0.f);  // smax2 = -1: fails "0 <= sigma2 <= smax2" for every pixel
+    rec[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Can the splat reach alpha >= 1/255 anywhere in the warp's block?  Two conservative tests:
 //  1. the integer-radius box written by the projection (outside it alpha < 1/255 by construction of the radius);
-//  2. the exact minimum of sigma(d) = .5(a dx^2 + c dy^2) + b dx dy over the block's pixel-centre rectangle against the
-//     record's sigma_max = ln(255 o) + margin — the same bound the per-pixel pre-test uses, so a culled splat would have
-//     failed that pre-test on every pixel of the block and the image is unchanged.  For anisotropic splats the box is
-//     several times larger than the ellipse; this test costs ~1 warp-instruction per (warp, splat) because 32 splats
-//     are tested per instruction, against ~35 (forward) / ~110 (backward) for an evaluation it avoids.
+//  2. the exact minimum of sigma2(d) = ha dx^2 + hc dy^2 + b2 dx dy over the block's pixel-centre rectangle against smax2 —
+//     the same bound the per-pixel pre-test uses, so a culled splat would have failed that pre-test on every pixel of the
+//     block and the image is unchanged.  ~1.5 warp-instructions per (warp, splat) because 32 splats are tested per
+//     instruction, against ~35 (forward) / ~55 (backward) for the evaluation it avoids.
 __device__ __forceinline__ bool splat_hits(const float4& A, const float4& B, const WarpRect& r) {
     const unsigned pr = __float_as_uint(B.w);
     // 65535 is the saturation value written by the projection: treat it as unbounded
     const float rx = (pr & 0xffffu) == 0xffffu ? 3.0e38f : (float)(pr & 0xffffu);
     const float ry = (pr >> 16) == 0xffffu ? 3.0e38f : (float)(pr >> 16);
     if (!((A.x + rx >= r.xlo) && (A.x - rx <= r.xhi) && (A.y + ry >= r.ylo) && (A.y - ry <= r.yhi))) return false;
-#ifndef ADB_NO_TIGHT_CULL
     const float x0 = r.xlo - A.x, x1 = r.xhi - A.x, y0 = r.ylo - A.y, y1 = r.yhi - A.y;
     if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;   // centre inside the block
-    const float a = A.z, b = A.w, c = B.x;
-    const float nb_c = -__fdividef(b, c), nb_a = -__fdividef(b, a);
+    const float ha = A.z, b = A.w, hc = B.x;
+    const float nb_c = -0.5f * __fdividef(b, hc), nb_a = -0.5f * __fdividef(b, ha);
     // minimum over each edge (1-D quadratic, minimiser clamped to the edge); the rectangle's minimum is on its boundary
     float m;
     {
         const float dy0 = fminf(y1, fmaxf(y0, nb_c * x0)), dy1 = fminf(y1, fmaxf(y0, nb_c * x1));
-        const float q0 = 0.5f * (a * x0 * x0 + c * dy0 * dy0) + b * x0 * dy0;
-        const float q1 = 0.5f * (a * x1 * x1 + c * dy1 * dy1) + b * x1 * dy1;
+        const float q0 = ha * x0 * x0 + hc * dy0 * dy0 + b * x0 * dy0;
+        const float q1 = ha * x1 * x1 + hc * dy1 * dy1 + b * x1 * dy1;
         m = fminf(q0, q1);
     }
     {
         const float dx0 = fminf(x1, fmaxf(x0, nb_a * y0)), dx1 = fminf(x1, fmaxf(x0, nb_a * y1));
-        const float q0 = 0.5f * (a * dx0 * dx0 + c * y0 * y0) + b * dx0 * y0;
-        const float q1 = 0.5f * (a * dx1 * dx1 + c * y1 * y1) + b * dx1 * y1;
+        const float q0 = ha * dx0 * dx0 + hc * y0 * y0 + b * dx0 * y0;
+        const float q1 = ha * dx1 * dx1 + hc * y1 * y1 + b * dx1 * y1;
         m = fminf(m, fminf(q0, q1));
     }
-    // rounding slack: the per-pixel test is sigma <= sigma_max in the same fp32 arithmetic
+    // rounding slack: the per-pixel test is sigma2 <= smax2 in the same fp32 arithmetic
     return m <= B.z * 1.0001f + 1e-4f;
-#else
-    return true;
-#endif
+}
+
+// Builds the warp's hit list for the staged batch (ascending slot order), padded to a multiple of 4 with DUMMY.
+// `limit`: only slots s with s >= limit are considered (the backward skips splats behind the warp's last contributor).
+__device__ __forceinline__ int build_hit_list(const float4* __restrict__ sRec, unsigned short* __restrict__ list,
+                                              int bsize, int limit, const WarpRect& rect, int lane) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int nhit = 0;
+    for (int c0 = (limit > 0 ? (limit & ~31) : 0); c0 < bsize; c0 += 32) {
+        const int s = c0 + lane;
+        bool hit = false;
+        if (s < bsize && s >= limit) hit = splat_hits(sRec[s * 3], sRec[s * 3 + 1], rect);
+        const unsigned mask = __ballot_sync(FULL, hit);
+        if (hit) list[nhit + __popc(mask & lt_mask)] = (unsigned short)s;
+        nhit += __popc(mask);
+    }
+    if (lane < 3) list[nhit + lane] = (unsigned short)DUMMY;
+    __syncwarp();
+    return nhit;
 }
 
 // LEGACY = Inria conventions (ADB_CONV_INRIA): alpha <= 0.99, stop when T(1-alpha) < 1e-4 (strict), 4th channel
 // accumulates 1/z, and main_ids gets the Gaussian with the largest blending weight alpha*T per pixel (-1: none).
 template <bool LEGACY>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* __restrict__ vals,
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
                  float* __restrict__ colors, float* __restrict__ alphas, int32_t* __restrict__ last_ids,
                  int32_t* __restrict__ main_ids) {
     constexpr float MAXA = LEGACY ? ADB_MAX_ALPHA_INRIA : ADB_MAX_ALPHA;
-    __shared__ float4 sA[BLOCK];
-    __shared__ float4 sB[BLOCK];
-    __shared__ float4 sC[BLOCK];
-    __shared__ unsigned char sList[BLOCK / 32][BLOCK];
+    __shared__ __align__(16) float4 sRec[(BLOCK + 1) * 3];
+    __shared__ __align__(8) unsigned short sList[NWARP][LIST_STRIDE];
 
     const int tw = (W + ADB_TILE - 1) / ADB_TILE;
     const int tile = blockIdx.y * tw + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int x0 = blockIdx.x * ADB_TILE + (warp & 1) * 8, y0 = blockIdx.y * ADB_TILE + (warp >> 1) * 4;
     const int j = x0 + (lane & 7), i = y0 + (lane >> 3);
     const bool inside = (i < H && j < W);
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const WarpRect rect{(float)x0 + 0.5f, (float)x0 + 7.5f, (float)y0 + 0.5f, (float)y0 + 3.5f};
     const int start = tile_offsets[tile], end = tile_offsets[tile + 1];
+    if (tid == 0) write_dummy(sRec + DUMMY * 3);
 
     float T = 1.0f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -109,52 +164,44 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     bool done = !inside;
     const int nb = (end - start + BLOCK - 1) / BLOCK;
     for (int b = 0; b < nb; ++b) {
-        if (__syncthreads_count(done) >= BLOCK) break;
+        if (__syncthreads_count(done) >= BLOCK) break;   // also: every warp has finished reading the previous batch
         const int bstart = start + b * BLOCK;
         const int idx = bstart + tid;
-        if (idx < end) {
-            gather_splat(splats, vals[idx] % n_per_cam, sA[tid], sB[tid], sC[tid]);
-            if (LEGACY) sC[tid].w = 1.0f / sC[tid].w;
-        }
+        if (idx < end) stage_record<LEGACY>(sRec + tid * 3, splats, vals[idx] % n_per_cam);
         __syncthreads();
         const int bsize = min(BLOCK, end - bstart);
         if (__all_sync(FULL, done)) continue;
-        // the warp's private hit list for this batch (ascending list order == front to back)
-        int nhit = 0;
-        for (int c0 = 0; c0 < bsize; c0 += 32) {
-            const int s = c0 + lane;
-            bool hit = false;
-            if (s < bsize) hit = splat_hits(sA[s], sB[s], rect);
-            const unsigned mask = __ballot_sync(FULL, hit);
-            if (hit) sList[warp][nhit + __popc(mask & lt_mask)] = (unsigned char)s;
-            nhit += __popc(mask);
-        }
-        __syncwarp();
-        for (int k = 0; k < nhit; ++k) {
-            const int t = sList[warp][k];
-            const float4 A = sA[t];
-            const float4 B = sB[t];
-            const float dx = A.x - px, dy = A.y - py;
-            const float sigma = 0.5f * (A.z * dx * dx + B.x * dy * dy) + A.w * dx * dy;
-            if (!done && sigma >= 0.f && sigma <= B.z) {
-                const float alpha = fminf(MAXA, B.y * __expf(-sigma));
-                if (alpha >= ADB_ALPHA_THRESHOLD) {
-                    const float nT = T * (1.0f - alpha);
-                    if (LEGACY ? (nT < ADB_T_EPS) : (nT <= ADB_T_EPS)) {
-                        done = true;
-                    } else {
-                        const float w = alpha * T;
-                        const float4 C = sC[t];
-                        acc.x += C.x * w; acc.y += C.y * w; acc.z += C.z * w; acc.w += C.w * w;
-                        cur = bstart + t;
-                        if (LEGACY && w > best_w) { best_w = w; best_k = cur; }
-                        T = nT;
-                    }
-                }
+        unsigned short* list = sList[warp];
+        const int nhit = build_hit_list(sRec, list, bsize, 0, rect, lane);
+        int cur_t = -1;
+        const int nq = (nhit + 3) >> 2;
+        for (int q = 0; q < nq; ++q) {
+            const uint2 pk = *reinterpret_cast<const uint2*>(list + 4 * q);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned w32 = (u < 2) ? pk.x : pk.y;
+                const int t = (u & 1) ? (int)(w32 >> 16) : (int)(w32 & 0xffffu);
+                const float4 A = sRec[t * 3], B = sRec[t * 3 + 1], C = sRec[t * 3 + 2];
+                const float dx = A.x - px, dy = A.y - py;
+                const float s2 = dx * (A.z * dx + A.w * dy) + (B.x * dy) * dy;
+                const float alpha = fminf(MAXA, B.y * ex2_approx(-s2));
+                const bool ok = !done && s2 >= 0.f && s2 <= B.z && alpha >= ADB_ALPHA_THRESHOLD;
+                const float nT = fmaf(-T, alpha, T);
+                const bool stop = ok && (LEGACY ? (nT < ADB_T_EPS) : (nT <= ADB_T_EPS));
+                const bool take = ok && !stop;
+                done = done || stop;
+                const float w = take ? alpha * T : 0.f;
+                acc.x = fmaf(C.x, w, acc.x);
+                acc.y = fmaf(C.y, w, acc.y);
+                acc.z = fmaf(C.z, w, acc.z);
+                acc.w = fmaf(C.w, w, acc.w);
+                cur_t = take ? t : cur_t;
+                if (LEGACY && w > best_w) { best_w = w; best_k = bstart + t; }
+                T = take ? nT : T;
             }
-            if ((k & 7) == 7 && __all_sync(FULL, done)) break;
+            if ((q & 1) && __all_sync(FULL, done)) break;
         }
-        __syncwarp();
+        if (cur_t >= 0) cur = bstart + cur_t;
     }
     if (inside) {
         const size_t pix = (size_t)i * W + j;
@@ -168,26 +215,45 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
 
-template <bool DIRECT, bool LEGACY>
-__global__ void __launch_bounds__(BLOCK)
+// Backward shared-memory layout (dynamic): S = slots per warp in the deferred-reduction buffer (16 or 32).
+template <int S>
+struct BwdSmem {
+    static constexpr int ROW4 = 17;                       // float4 per slot row: 32 x (vs, fac) + 1 pad -> conflict-free
+    static constexpr int OFF_REC = 0;                     // float4 [(BLOCK+1)*3]
+    static constexpr int OFF_G = OFF_REC + (BLOCK + 1) * 3 * 16;             // int [BLOCK + 4]
+    static constexpr int OFF_LIST = OFF_G + (BLOCK + 4) * 4;                  // u16 [NWARP][LIST_STRIDE]
+    static constexpr int OFF_VO = OFF_LIST + NWARP * LIST_STRIDE * 2;         // float4 [NWARP][32]
+    static constexpr int OFF_V = OFF_VO + NWARP * 32 * 16;                    // float4 [NWARP][S*ROW4]
+    static constexpr int BYTES = OFF_V + NWARP * S * ROW4 * 16;
+    static_assert(OFF_G % 16 == 0 && OFF_LIST % 16 == 0 && OFF_VO % 16 == 0 && OFF_V % 16 == 0, "alignment");
+};
+
+template <bool LEGACY, int S>
+__global__ void __launch_bounds__(BLOCK, 3)
 blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* __restrict__ vals,
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
                  const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
                  const float* __restrict__ v_colors, const float* __restrict__ v_alphas,
                  float* __restrict__ v_splats) {
     constexpr float MAXA = LEGACY ? ADB_MAX_ALPHA_INRIA : ADB_MAX_ALPHA;
-    __shared__ float4 sA[BLOCK];
-    __shared__ float4 sB[BLOCK];
-    __shared__ float4 sC[BLOCK];
-    __shared__ int sG[BLOCK];
-    __shared__ unsigned char sList[BLOCK / 32][BLOCK];
-    __shared__ __align__(16) float sAcc[BLOCK][12];
+    using L = BwdSmem<S>;
+    constexpr int HALVES = 32 / S;          // lanes per slot in the reduction phase
+    constexpr int ROWS = 4 / HALVES;        // pixel rows (of 8) each reduction lane walks
+    static_assert(S == 16 || S == 32, "S");
+    extern __shared__ __align__(16) unsigned char smem[];
+    float4* sRec = reinterpret_cast<float4*>(smem + L::OFF_REC);
+    int* sG = reinterpret_cast<int*>(smem + L::OFF_G);
 
     const int tw = (W + ADB_TILE - 1) / ADB_TILE;
     const int tile = blockIdx.y * tw + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned short* list = reinterpret_cast<unsigned short*>(smem + L::OFF_LIST) + warp * LIST_STRIDE;
+    float4* sVo = reinterpret_cast<float4*>(smem + L::OFF_VO) + warp * 32;
+    float4* sV = reinterpret_cast<float4*>(smem + L::OFF_V) + warp * S * L::ROW4;
     const int x0 = blockIdx.x * ADB_TILE + (warp & 1) * 8, y0 = blockIdx.y * ADB_TILE + (warp >> 1) * 4;
     const int j = x0 + (lane & 7), i = y0 + (lane >> 3);
     const bool inside = (i < H && j < W);
@@ -204,135 +270,122 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     float T = T_final;
     float bv = 0.f;
     const float Tva = T_final * va;
+    sVo[lane] = vo;
+    if (tid == 0) { write_dummy(sRec + DUMMY * 3); sG[DUMMY] = 0; }
 
     int warp_bin_final = bin_final;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(FULL, warp_bin_final, o));
 
-    // which of the 10 reduced components this lane ends up owning after the packed butterfly (-1: none)
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-    int my_comp = (b4 ? 5 : 0) + (b3 ? 3 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
-    if ((lane & 1) || (b2 && b1) || (b3 && b2)) my_comp = -1;
+    // reduction-phase role of this lane: slot r_slot, pixel rows [r_half*ROWS, +ROWS) of the warp's 8x4 block
+    const int r_slot = lane & (S - 1), r_half = lane / S;
+    const float4* r_row = sV + r_slot * L::ROW4 + r_half * (ROWS * 4);
+    const float4* r_vo = sVo + r_half * (ROWS * 8);
+    float2* my_cell = reinterpret_cast<float2*>(sV) + lane;          // + slot * ROW4 * 2 (float2 units)
 
     const int nb = (end - start + BLOCK - 1) / BLOCK;
     for (int b = 0; b < nb; ++b) {
-        __syncthreads();  // previous batch fully consumed / flushed
-        const int batch_end = end - 1 - b * BLOCK;
+        __syncthreads();  // previous batch fully consumed
+        const int batch_end = end - 1 - b * BLOCK;           // smem slot t <-> sorted index batch_end - t (back to front)
         const int bsize = min(BLOCK, batch_end + 1 - start);
         const int idx = batch_end - tid;
         if (idx >= start) {
             const int g = vals[idx] % n_per_cam;
             sG[tid] = g;
-            gather_splat(splats, g, sA[tid], sB[tid], sC[tid]);
-            if (LEGACY) sC[tid].w = 1.0f / sC[tid].w;   // v_splats slot 9 is then dL/d(1/z)
-        }
-        if (!DIRECT) {
-            float4* z = reinterpret_cast<float4*>(sAcc[tid]);
-            z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            stage_record<LEGACY>(sRec + tid * 3, splats, g);
         }
         __syncthreads();
-        // (a warp whose last contributing splat lies before this whole batch has every `hit` false below)
-        int nhit = 0;
-        for (int c0 = 0; c0 < bsize; c0 += 32) {
-            if (batch_end - (c0 + 31) > warp_bin_final) continue;  // chunk entirely behind this warp's last splat
-            const int s = c0 + lane;
-            bool hit = false;
-            if (s < bsize && batch_end - s <= warp_bin_final) hit = splat_hits(sA[s], sB[s], rect);
-            const unsigned mask = __ballot_sync(FULL, hit);
-            if (hit) sList[warp][nhit + __popc(mask & lt_mask)] = (unsigned char)s;
-            nhit += __popc(mask);
-        }
-        __syncwarp();
-        {
-            for (int k = 0; k < nhit; ++k) {
-                const int t = sList[warp][k];
-                const float4 A = sA[t];
-                const float4 B = sB[t];
-                const float dx = A.x - px, dy = A.y - py;
-                const float sigma = 0.5f * (A.z * dx * dx + B.x * dy * dy) + A.w * dx * dy;
-                bool valid = inside && (batch_end - t <= bin_final) && sigma >= 0.f && sigma <= B.z;
-                float vis = 0.f, alpha = 0.f;
-                if (valid) {
-                    vis = __expf(-sigma);
-                    alpha = fminf(MAXA, B.y * vis);
-                    valid = alpha >= ADB_ALPHA_THRESHOLD;
-                }
-                if (!__any_sync(FULL, valid)) continue;
-                // Branch-free from here: an invalid lane runs with alpha = vis = 0, which leaves T and bv unchanged
-                // (ra = 1, fac = 0) and contributes exact zeros to every sum.
-                alpha = valid ? alpha : 0.f;
-                vis = valid ? vis : 0.f;
-                float v[10];
-                {
-                    const float4 C = sC[t];
-                    const float ra = __fdividef(1.0f, 1.0f - alpha);
+        // a splat at slot s contributes to this warp only if batch_end - s <= warp_bin_final
+        const int limit = max(0, batch_end - warp_bin_final);
+        if (limit >= bsize) continue;
+        const int nhit = build_hit_list(sRec, list, bsize, limit, rect, lane);
+        const int tmin = inside ? batch_end - bin_final : (1 << 30);   // lane-valid iff t >= tmin
+        for (int g0 = 0; g0 < nhit; g0 += S) {
+            const int ng = min(S, nhit - g0);
+            const int nq = (ng + 3) >> 2;
+            for (int q = 0; q < nq; ++q) {
+                const uint2 pk = *reinterpret_cast<const uint2*>(list + g0 + 4 * q);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned w32 = (u < 2) ? pk.x : pk.y;
+                    const int t = (u & 1) ? (int)(w32 >> 16) : (int)(w32 & 0xffffu);
+                    const float4 A = sRec[t * 3], B = sRec[t * 3 + 1], C = sRec[t * 3 + 2];
+                    const float dx = A.x - px, dy = A.y - py;
+                    const float s2 = dx * (A.z * dx + A.w * dy) + (B.x * dy) * dy;
+                    const float ov = B.y * ex2_approx(-s2);
+                    const float am = fminf(MAXA, ov);
+                    const bool valid = t >= tmin && s2 >= 0.f && s2 <= B.z && am >= ADB_ALPHA_THRESHOLD;
+                    // An invalid lane runs with alpha = 0, which leaves T and bv unchanged (ra = 1, fac = 0) and
+                    // contributes exact zeros to every sum.
+                    const float alpha = valid ? am : 0.f;
+                    const float ra = rcp_approx(1.0f - alpha);
                     T *= ra;
                     const float fac = alpha * T;
-                    // cv = <feat, v_out>;  bv = sum over later splats of fac*cv  (the scalar the 4-channel
-                    // "buffer" of the textbook backward collapses to once it is dotted with v_out)
-                    const float cv = C.x * vo.x + C.y * vo.y + C.z * vo.z + C.w * vo.w;
-                    const float v_alpha = cv * T + (Tva - bv) * ra;
-                    bv += fac * cv;
-                    v[6] = fac * vo.x; v[7] = fac * vo.y; v[8] = fac * vo.z; v[9] = fac * vo.w;
-                    // d(alpha)/d(sigma) path is cut where alpha was clamped to 0.999
-                    const float ov = B.y * vis;
-                    const float v_sigma = ov <= MAXA ? -ov * v_alpha : 0.f;
-                    // raw moments of v_sigma about the splat centre; project_bwd turns them into
-                    // v_mean2d / v_conic / v_opacity once per Gaussian instead of once per pair
-                    v[5] = v_sigma;
-                    v[0] = v_sigma * dx;
-                    v[1] = v_sigma * dy;
-                    v[2] = v[0] * dx;
-                    v[3] = v[0] * dy;
-                    v[4] = v[1] * dy;
-                }
-                // packed butterfly: 10 values -> 5 -> 3 -> 2 -> 1 -> 1  (12 shuffles)
-                float w0, w1, w2, w3, w4;
-                {
-                    float s0 = b4 ? v[0] : v[5], k0 = b4 ? v[5] : v[0];
-                    float s1 = b4 ? v[1] : v[6], k1 = b4 ? v[6] : v[1];
-                    float s2 = b4 ? v[2] : v[7], k2 = b4 ? v[7] : v[2];
-                    float s3 = b4 ? v[3] : v[8], k3 = b4 ? v[8] : v[3];
-                    float s4 = b4 ? v[4] : v[9], k4 = b4 ? v[9] : v[4];
-                    w0 = k0 + __shfl_xor_sync(FULL, s0, 16);
-                    w1 = k1 + __shfl_xor_sync(FULL, s1, 16);
-                    w2 = k2 + __shfl_xor_sync(FULL, s2, 16);
-                    w3 = k3 + __shfl_xor_sync(FULL, s3, 16);
-                    w4 = k4 + __shfl_xor_sync(FULL, s4, 16);
-                }
-                float u0, u1, u2;
-                {
-                    float s0 = b3 ? w0 : w3, k0 = b3 ? w3 : w0;
-                    float s1 = b3 ? w1 : w4, k1 = b3 ? w4 : w1;
-                    float s2 = b3 ? w2 : 0.f, k2 = b3 ? 0.f : w2;
-                    u0 = k0 + __shfl_xor_sync(FULL, s0, 8);
-                    u1 = k1 + __shfl_xor_sync(FULL, s1, 8);
-                    u2 = k2 + __shfl_xor_sync(FULL, s2, 8);
-                }
-                float t0, t1;
-                {
-                    float s0 = b2 ? u0 : u2, k0 = b2 ? u2 : u0;
-                    float s1 = b2 ? u1 : 0.f, k1 = b2 ? 0.f : u1;
-                    t0 = k0 + __shfl_xor_sync(FULL, s0, 4);
-                    t1 = k1 + __shfl_xor_sync(FULL, s1, 4);
-                }
-                float r = (b1 ? t1 : t0) + __shfl_xor_sync(FULL, b1 ? t0 : t1, 2);
-                r += __shfl_xor_sync(FULL, r, 1);
-                if (my_comp >= 0) {
-                    if (DIRECT) atomicAdd(v_splats + (size_t)sG[t] * ADB_SPLAT_STRIDE + my_comp, r);
-                    else atomicAdd(&sAcc[t][my_comp], r);
+                    // cv = <feat, v_out>;  bv = sum over later splats of fac*cv  (the scalar the 4-channel "buffer" of
+                    // the textbook backward collapses to once it is dotted with v_out)
+                    const float cv = fmaf(C.x, vo.x, fmaf(C.y, vo.y, fmaf(C.z, vo.z, C.w * vo.w)));
+                    const float v_alpha = fmaf(cv, T, (Tva - bv) * ra);
+                    bv = fmaf(fac, cv, bv);
+                    // d(alpha)/d(sigma) = -o exp(-sigma); the path is cut where alpha was clamped
+                    const float nov = (valid && ov <= MAXA) ? -ov : 0.f;
+                    my_cell[(4 * q + u) * (L::ROW4 * 2)] = make_float2(nov * v_alpha, fac);
                 }
             }
-        }
-        if (DIRECT) continue;
-        __syncthreads();
-        if (tid < bsize) {
-            const float4* a = reinterpret_cast<const float4*>(sAcc[tid]);
-            const float4 q0 = a[0], q1 = a[1], q2 = a[2];
-            float* dst = v_splats + (size_t)sG[tid] * ADB_SPLAT_STRIDE;
-            if (q0.x != 0.f || q0.y != 0.f || q0.z != 0.f || q0.w != 0.f) red_add_v4(dst, q0.x, q0.y, q0.z, q0.w);
-            if (q1.x != 0.f || q1.y != 0.f || q1.z != 0.f || q1.w != 0.f) red_add_v4(dst + 4, q1.x, q1.y, q1.z, q1.w);
-            if (q2.x != 0.f || q2.y != 0.f) red_add_v4(dst + 8, q2.x, q2.y, 0.f, 0.f);
+            __syncwarp();
+            // ---- deferred reduction: lane = (slot, pixel-row group) ----
+            float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                float R0 = 0.f, R1 = 0.f, R2 = 0.f;
+#pragma unroll
+                for (int x = 0; x < 8; x += 2) {
+                    const float4 v = r_row[r * 4 + x / 2];          // (vs, fac) of pixels (x, r) and (x+1, r)
+                    const float4 w0 = r_vo[r * 8 + x], w1 = r_vo[r * 8 + x + 1];
+                    R0 += v.x;
+                    R1 = fmaf(v.x, (float)x, R1);
+                    R2 = fmaf(v.x, (float)(x * x), R2);
+                    c0 = fmaf(v.y, w0.x, c0); c1 = fmaf(v.y, w0.y, c1); c2 = fmaf(v.y, w0.z, c2); c3 = fmaf(v.y, w0.w, c3);
+                    R0 += v.z;
+                    R1 = fmaf(v.z, (float)(x + 1), R1);
+                    R2 = fmaf(v.z, (float)((x + 1) * (x + 1)), R2);
+                    c0 = fmaf(v.w, w1.x, c0); c1 = fmaf(v.w, w1.y, c1); c2 = fmaf(v.w, w1.z, c2); c3 = fmaf(v.w, w1.w, c3);
+                }
+                const float ly = (float)(r_half * ROWS + r);
+                S0 += R0; Sx += R1; Sxx += R2;
+                Sy = fmaf(ly, R0, Sy); Sxy = fmaf(ly, R1, Sxy); Syy = fmaf(ly * ly, R0, Syy);
+            }
+            if (HALVES == 2) {
+                S0 += __shfl_xor_sync(FULL, S0, 16); Sx += __shfl_xor_sync(FULL, Sx, 16);
+                Sy += __shfl_xor_sync(FULL, Sy, 16); Sxx += __shfl_xor_sync(FULL, Sxx, 16);
+                Sxy += __shfl_xor_sync(FULL, Sxy, 16); Syy += __shfl_xor_sync(FULL, Syy, 16);
+                c0 += __shfl_xor_sync(FULL, c0, 16); c1 += __shfl_xor_sync(FULL, c1, 16);
+                c2 += __shfl_xor_sync(FULL, c2, 16); c3 += __shfl_xor_sync(FULL, c3, 16);
+            }
+            if (r_slot < ng) {
+                const int t = list[g0 + r_slot];
+                const float4 A = sRec[t * 3];
+                float* dst = v_splats + (size_t)sG[t] * ADB_SPLAT_STRIDE;
+                // dx = ex - lx, dy = ey - ly with (lx, ly) the integer pixel offset inside the block
+                const float ex = A.x - rect.xlo, ey = A.y - rect.ylo;
+                if (r_half == 0) {
+                    if (S0 != 0.f || Sx != 0.f || Sy != 0.f || Sxx != 0.f || Sxy != 0.f) {
+                        const float Mx = fmaf(ex, S0, -Sx), My = fmaf(ey, S0, -Sy);
+                        const float Mxx = fmaf(ex, fmaf(ex, S0, -2.f * Sx), Sxx);
+                        const float Mxy = fmaf(ex, My, fmaf(-ey, Sx, Sxy));
+                        red_add_v4(dst, Mx, My, Mxx, Mxy);
+                    }
+                    if (HALVES == 1) {
+                        const float Myy = fmaf(ey, fmaf(ey, S0, -2.f * Sy), Syy);
+                        if (Myy != 0.f || S0 != 0.f || c0 != 0.f || c1 != 0.f) red_add_v4(dst + 4, Myy, S0, c0, c1);
+                        if (c2 != 0.f || c3 != 0.f) red_add_v2(dst + 8, c2, c3);
+                    }
+                } else {
+                    const float Myy = fmaf(ey, fmaf(ey, S0, -2.f * Sy), Syy);
+                    if (Myy != 0.f || S0 != 0.f || c0 != 0.f || c1 != 0.f) red_add_v4(dst + 4, Myy, S0, c0, c1);
+                    if (c2 != 0.f || c3 != 0.f) red_add_v2(dst + 8, c2, c3);
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -371,6 +424,22 @@ ADB_API int adb_raster_blend_fwd_legacy(int W, int H, int n_per_cam, const float
                           stream);
 }
 
+template <bool LEGACY, int S>
+static int launch_bwd(dim3 grid, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                      const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids, const float* v_colors,
+                      const float* v_alphas, float* v_splats, cudaStream_t stream) {
+    static AdbDeviceOnce once;
+    const int rc = once.ensure([]() -> int {
+        ADB_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<LEGACY, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      BwdSmem<S>::BYTES));
+        return ADB_OK;
+    });
+    if (rc != ADB_OK) return rc;
+    blend_bwd_kernel<LEGACY, S><<<grid, BLOCK, BwdSmem<S>::BYTES, stream>>>(
+        W, H, splats, vals_sorted, tile_offsets, n_per_cam, alphas, last_ids, v_colors, v_alphas, v_splats);
+    return ADB_OK;
+}
+
 static int blend_bwd_impl(bool legacy, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
                           const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
                           const float* v_colors, const float* v_alphas, float* v_splats, cudaStream_t stream) {
@@ -379,16 +448,19 @@ static int blend_bwd_impl(bool legacy, int W, int H, int n_per_cam, const float*
     if (n_per_cam == 0) return ADB_OK;
     ADB_REQUIRE(v_splats, "adb_raster_blend_bwd: null v_splats");
     dim3 grid(adb_cdiv(W, ADB_TILE), adb_cdiv(H, ADB_TILE));
-    static const int mode = getenv("ADB_BWD_MODE") ? atoi(getenv("ADB_BWD_MODE")) : 0;
+    // ADB_BWD_SLOTS=32: 32-slot deferred-reduction buffer (A/B switch; 16 keeps 3 CTAs per SM)
+    static const int slots = getenv("ADB_BWD_SLOTS") ? atoi(getenv("ADB_BWD_SLOTS")) : 16;
+    int rc;
     if (legacy)
-        blend_bwd_kernel<false, true><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, n_per_cam,
-                                                                 alphas, last_ids, v_colors, v_alphas, v_splats);
-    else if (mode == 1)
-        blend_bwd_kernel<true, false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, n_per_cam,
-                                                                 alphas, last_ids, v_colors, v_alphas, v_splats);
+        rc = launch_bwd<true, 16>(grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
+                                  v_alphas, v_splats, stream);
+    else if (slots == 32)
+        rc = launch_bwd<false, 32>(grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
+                                   v_alphas, v_splats, stream);
     else
-        blend_bwd_kernel<false, false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, n_per_cam,
-                                                                  alphas, last_ids, v_colors, v_alphas, v_splats);
+        rc = launch_bwd<false, 16>(grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
+                                   v_alphas, v_splats, stream);
+    if (rc != ADB_OK) return rc;
     ADB_CHECK_LAUNCH("blend_bwd_kernel");
     return ADB_OK;
 }

@@ -92,14 +92,13 @@ class _RasterizeLegacy(torch.autograd.Function):
         return (v_means, v_means2D, v_quats, v_scales, v_opac, v_sh, v_view, None, v_campos, None, None, None)
 
 
-def _intrinsics(s: GaussianRasterizationSettings, viewmat: torch.Tensor) -> torch.Tensor:
-    """K from the settings, built on the device (no host sync): focal from tanfov as Inria's Jacobian does, principal
-    point from the projection matrix (P = full_proj @ inv(view); P[0,2] = (2cx-W)/W), which is W/2, H/2 for the
-    symmetric frustum the reference builds (Reconstruct/utils.py:154-178)."""
+def _intrinsics(s: GaussianRasterizationSettings, dev: torch.device) -> torch.Tensor:
+    """K from the settings, built on the device (no host sync).  ``projmatrix`` is the transposed PROJECTION-ONLY matrix,
+    exactly what the reference's only call site passes (Reconstruct/webviewer/scene_models.py:549-566,881-887:
+    ``getProjectionMatrix2(...).transpose(0,1)``; the view matrix comes per call).  Focal from tanfov as Inria's Jacobian
+    uses it; principal point from P[0,2] = (2cx-W)/W, P[1,2] = (2cy-H)/H (Reconstruct/utils.py:133-154)."""
     W, H = int(s.image_width), int(s.image_height)
-    dev = viewmat.device
-    full = _f32c(s.projmatrix.to(dev)).t()
-    P = full @ torch.inverse(viewmat)
+    P = _f32c(s.projmatrix.to(dev)).t()
     K = torch.zeros(3, 3, dtype=torch.float32, device=dev)
     K[0, 0] = W / (2.0 * float(s.tanfovx))
     K[1, 1] = H / (2.0 * float(s.tanfovy))
@@ -129,7 +128,7 @@ def rasterize_gaussians(means3D, means2D, opacities, dc, shs, scales, rotations,
         sh = torch.cat([sh, sh.new_zeros(N, 16 - sh.shape[1], 3)], 1) if sh.shape[1] < 16 else sh[:, :16]
     sh = sh.contiguous()
     V = _f32c(viewmatrix).t().contiguous()       # the legacy API passes the transposed world->camera matrix
-    K = _intrinsics(s, V.detach()).detach()
+    K = _intrinsics(s, dev).detach()
     campos = _f32c(s.campos.to(dev)).reshape(3)
     if means2D is None:
         means2D = torch.zeros(N, 3, dtype=torch.float32, device=dev)

@@ -3,6 +3,8 @@ companions.  A "split" activation is a pair of bf16 tensors (hi, lo) with x ~= h
 the pair directly so GEMM operands never make a separate conversion pass."""
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from .. import _lib
@@ -12,6 +14,7 @@ _lib.register("adb_gemm_bf16", [i32, i32, i32, i32, vp, vp, i64, i64, vp, vp, i6
                                 vp, vp, i64, i64, f32, i32, i32, i64, i64, i64, vp])
 _lib.register("adb_conv3x3_bf16", [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp])
 _lib.register("adb_attention_bf16", [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp])
+_lib.register("adb_attention_set_variant", [i32])
 _lib.register("adb_layernorm", [i64, i32, vp, vp, vp, f32, vp, vp, vp, vp])
 _lib.register("adb_split_bf16", [i64, vp, vp, vp, vp])
 _lib.register("adb_rope_heads", [i32, i32, i32, i64, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp])
@@ -193,6 +196,14 @@ def conv3x3(x: Split, B: int, H: int, W: int, Cin: int, w: Split, bias, Cout: in
               _lib.ptr(sp.hi) if sp is not None else None,
               _lib.ptr(sp.lo) if (sp is not None and sp.lo is not None) else None, int(act), int(split_relu), _lib.stream())
     return out, sp
+
+
+def set_attention_variant(variant: int) -> int:
+    """0 = automatic (default), 1 / 2 force a kernel variant (csrc/attn_tc.cu).  Returns the previous setting."""
+    prev = _lib.lib().adb_attention_set_variant(C.c_int(int(variant)))   # returns the previous value, not a status
+    if prev < 0:
+        raise ValueError("attention variant must be 0, 1 or 2")
+    return prev
 
 
 def attention(q: Split, k: Split, vt: Split, B: int, h: int, Nq: int, Nk: int, Nkpad: int, scale: float, x3=True) -> Split:

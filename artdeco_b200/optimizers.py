@@ -34,6 +34,22 @@ def _is_empty(t: torch.Tensor) -> bool:
     return t.numel() == 0 or t.dim() == 0
 
 
+def _check_sparse_args(key, param, grad, m1, m2, visibility, N, M):
+    """The raw-pointer launches below trust these shapes; a stale mask after densify must raise (the reference's boolean
+    indexing raises IndexError in the same situation) instead of reading or writing out of bounds on the device."""
+    if N * M != param.numel():
+        raise ValueError(f"SparseGaussianAdam[{key}]: param has {param.numel()} elements, expected N*M = {N}*{M}")
+    if visibility is None or visibility.dtype not in (torch.bool, torch.uint8) or visibility.numel() != N:
+        got = None if visibility is None else (visibility.dtype, visibility.numel())
+        raise IndexError(f"SparseGaussianAdam[{key}]: visibility must be a bool/uint8 tensor with N={N} elements, got {got}")
+    for name, t in (("param", param), ("grad", grad), ("exp_avg", m1), ("exp_avg_sq", m2)):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != N * M or t.device != param.device:
+            raise ValueError(f"SparseGaussianAdam[{key}]: {name} must be a contiguous float32 tensor of {N * M} elements "
+                             f"on {param.device}")
+    if visibility.device != param.device:
+        raise ValueError(f"SparseGaussianAdam[{key}]: visibility is on {visibility.device}, params on {param.device}")
+
+
 def compact_plan(valid_mask: torch.Tensor):
     """Returns (src_of int32 [N], n_keep).  One host sync (the count), like the first boolean index in the reference."""
     _lib.require_cuda(valid_mask)
@@ -53,10 +69,12 @@ def compact_plan(valid_mask: torch.Tensor):
     return src_of, int(cnt.item())
 
 
-def compact_gather(src_of, n_keep: int, n_ext: int, jobs):
+def compact_gather(src_of, n_keep: int, n_ext: int, jobs, n_mask: int | None = None):
     """jobs: list of (src [N,...], ext [n_ext,...] | None, fill, tail_shape) -> list of outputs [n_keep+n_ext, *tail_shape].
     ``ext is None`` fills the n_ext tail rows with ``fill`` (no extension buffer is materialised)."""
     outs = []
+    if n_mask is None:
+        n_mask = int(src_of.numel())
     for j0 in range(0, len(jobs), MAX_TENSORS):
         chunk = jobs[j0:j0 + MAX_TENSORS]
         n = len(chunk)
@@ -68,6 +86,11 @@ def compact_gather(src_of, n_keep: int, n_ext: int, jobs):
             dtype = src.dtype
             if src.numel() and tuple(src.shape[1:]) != tail:
                 raise ValueError(f"state rows {tuple(src.shape[1:])} do not match the extension rows {tail}")
+            if src.numel() and src.shape[0] != n_mask:
+                raise IndexError(f"compact_gather: state tensor has {src.shape[0]} rows but the mask has {n_mask} "
+                                 "(stale valid_mask after a densification?)")
+            if ext is not None and ext.numel() and (ext.shape[0] != n_ext or tuple(ext.shape[1:]) != tail):
+                raise ValueError(f"compact_gather: extension shape {tuple(ext.shape)} != ({n_ext}, *{tail})")
             if dtype not in (torch.float32, torch.int64, torch.int32):
                 raise TypeError(f"compact_gather: unsupported dtype {dtype}")
             src = src.contiguous()
@@ -147,6 +170,7 @@ class SparseGaussianAdam(BaseAdam):
         if key in self.lr_dict and lr.numel() == param.numel() and lr.is_contiguous() and lr.dtype == torch.float32:
             cfg = self.lr_dict[key]
             grad = param.grad.contiguous()
+            _check_sparse_args(key, param, grad, param_dict["exp_avg"], param_dict["exp_avg_sq"], visibility, N, M)
             vis = visibility.contiguous()
             with torch.cuda.device(param.device):
                 _lib.call("adb_adam_update_decay", N, M, _lib.ptr(param), _lib.ptr(grad), _lib.ptr(param_dict["exp_avg"]),
@@ -221,7 +245,7 @@ class SparseGaussianAdam(BaseAdam):
                 if key in self.lr_dict:                                   # cat(lr[mask], ones_like(ext) * lr_init)
                     jobs.append((param["lr"], None, self.lr_dict[key]["lr_init"], tail))
                     slots.append((key, "lr"))
-            outs = compact_gather(src_of, n_keep, n_ext, jobs)
+            outs = compact_gather(src_of, n_keep, n_ext, jobs, n_mask=int(valid_mask.numel()))
             for (key, slot), out in zip(slots, outs):
                 self.params[key][slot] = out
                 if slot == "val" and key not in _NO_MOMENTS:

@@ -25,6 +25,8 @@ _lib.register("adb_raster_isect_emit", [i32, vp, vp, vp, i32, i32, i32, i32, vp,
 _lib.register("adb_raster_sort_workspace_bytes", [i64, C.POINTER(C.c_size_t)])
 _lib.register("adb_raster_sort", [i64, i32, i32, i32, vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_int), vp])
 _lib.register("adb_raster_tile_offsets", [i64, vp, i32, i32, vp, vp])
+_lib.register("adb_raster_tile_count_scan", [i32, vp, vp, vp, i32, i32, i32, i64, vp, vp, vp, vp, vp])
+_lib.register("adb_raster_tile_scatter_sort", [i32, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp])
 _lib.register("adb_raster_blend_fwd", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp])
 _lib.register("adb_raster_blend_bwd", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 _lib.register("adb_raster_project_bwd", [i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32,
@@ -78,16 +80,62 @@ def project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, 
     return radii, splats, tpg
 
 
-def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=False):
-    """Tile keys/values (sorted), tile offsets [T+1].  One host sync (reads the intersection count)."""
+def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=False, capacity=None, method=None):
+    """Tile keys/values (sorted), tile offsets [T+1] for one camera.
+
+    ``method="bucket"`` (default): tile-bucketed pipeline — count, scan, scatter, one CTA-local bitonic sort per tile
+    (csrc/raster_isect.cu) — bit-identical to the stable radix sort of (cam | tile | depth) keys it replaces.
+    ``method="radix"`` (or env ADB_ISECT=radix): round-1 path (scan, emit, CUB onesweep radix sort, offsets), kept for A/B.
+
+    ``capacity=None``: one host sync to size keys/vals exactly (gsplat does the same: ``cum_tiles[-1].item()``);
+    returns ``(keys[I], vals[I], offsets, I:int)``.
+    ``capacity=int``: NO host sync (CUDA-graph capturable): buffers hold ``capacity`` intersections, the true count and an
+    overflow flag stay on the device; returns ``(keys[capacity], vals[capacity], offsets, info)`` with
+    ``info = {"n_isect": int64[1] tensor, "overflow": int32[1] tensor}``; entries beyond ``offsets[T]`` are undefined.  On
+    overflow the dropped intersections make the image wrong but nothing is written out of bounds."""
     N = radii.shape[0]
     dev = radii.device
     T = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
+    if method is None:
+        import os
+        method = os.environ.get("ADB_ISECT", "bucket")
     offsets = torch.empty(T + 1, dtype=torch.int32, device=dev)
     if N == 0:
         offsets.zero_()
         e64 = torch.empty(0, dtype=torch.int64, device=dev)
-        return e64, torch.empty(0, dtype=torch.int32, device=dev), offsets, 0
+        e32 = torch.empty(0, dtype=torch.int32, device=dev)
+        if capacity is None:
+            return e64, e32, offsets, 0
+        return e64, e32, offsets, {"n_isect": torch.zeros(1, dtype=torch.int64, device=dev),
+                                   "overflow": torch.zeros(1, dtype=torch.int32, device=dev)}
+    if method == "bucket" and sort:
+        counts = torch.zeros(T, dtype=torch.int32, device=dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        cap_scan = int(capacity) if capacity is not None else 2147483646
+        _lib.call("adb_raster_tile_count_scan", N, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), W, H, int(legacy),
+                  cap_scan, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(total), _lib.ptr(overflow), _lib.stream())
+        if capacity is None:
+            n_isect = int(total.item())      # the pipeline's single host sync
+            if n_isect >= 2147483647:
+                raise _lib.ArtdecoB200Error("more than 2^31 tile intersections")
+            cap = n_isect
+        else:
+            cap = int(capacity)
+        keys = torch.empty(max(cap, 1), dtype=torch.int64, device=dev)
+        vals = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        if cap > 0:
+            packed = torch.empty(cap, dtype=torch.int64, device=dev)
+            _lib.call("adb_raster_tile_scatter_sort", N, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), W, H,
+                      int(legacy), cam_id, n_cams, cap, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(packed),
+                      _lib.ptr(keys), _lib.ptr(vals), _lib.stream())
+        else:
+            counts.zero_()
+        if capacity is None:
+            return keys[:n_isect], vals[:n_isect], offsets, n_isect
+        return keys[:cap], vals[:cap], offsets, {"n_isect": total, "overflow": overflow}
+    if capacity is not None:
+        raise NotImplementedError("capacity mode needs method='bucket'")
     nb = C.c_size_t(0)
     _lib.call("adb_raster_scan_workspace_bytes", N, C.byref(nb))
     cum = torch.empty(N, dtype=torch.int64, device=dev)

@@ -85,6 +85,10 @@ class _FusedSSIMMean(torch.autograd.Function):
     @staticmethod
     def forward(ctx, C1, C2, img1, img2, train):
         _lib.require_cuda(img1)
+        if tuple(img2.shape) != tuple(img1.shape):
+            raise ValueError(f"fused_ssim: img1 {tuple(img1.shape)} and img2 {tuple(img2.shape)} must have the same shape")
+        if not img2.is_cuda or img2.device != img1.device:
+            raise ValueError(f"fused_ssim: img2 must be a CUDA tensor on {img1.device}, got {img2.device}")
         img2 = img2.contiguous()
         B, CH, H, W = _dims(img1)
         acc = torch.zeros(1, dtype=torch.float32, device=img1.device)

@@ -57,6 +57,21 @@ int adb_raster_sort(long long n_isect, int W, int H, int n_cams, int64_t* keys_a
                     int32_t* vals_b, void* ws, size_t ws_bytes, int* sorted_in_b /*HOST*/, adb_stream_t stream);
 int adb_raster_tile_offsets(long long n_isect, const int64_t* keys_sorted, int W, int H,
                             int32_t* tile_offsets /*[T+1]*/, adb_stream_t stream);
+/* Tile-bucketed intersection (no library sort, no host sync; bit-identical to adb_raster_isect_emit + adb_raster_sort +
+ * adb_raster_tile_offsets, i.e. to gsplat's isect_tiles / radix sort / isect_offset_encode behind h3dgsv3.py:664-680):
+ *   adb_raster_tile_count_scan   per-tile counts (RED.ADD) + one-CTA exclusive scan -> tile_offsets[T+1] clamped to
+ *                                `capacity`; *total (int64, device) = true intersection count, *overflow (int32, device)
+ *                                is SET when total > capacity.  tile_counts[T] must be zero on entry.
+ *   adb_raster_tile_scatter_sort scatter depth_bits<<32|gaussian into each tile's segment (counters return to zero), then
+ *                                one CTA per tile sorts its segment (bitonic, shared memory; global memory beyond 4096
+ *                                entries) and writes keys = cam|tile|depth_bits, vals = cam*N + gaussian.
+ * packed: uint64[capacity] scratch.  legacy != 0 selects the Inria tile rectangle. */
+int adb_raster_tile_count_scan(int N, const int32_t* radii, const float* splats, const int32_t* tiles_per_gauss, int W, int H,
+                               int legacy, long long capacity, int32_t* tile_counts, int32_t* tile_offsets, long long* total,
+                               int32_t* overflow, adb_stream_t stream);
+int adb_raster_tile_scatter_sort(int N, const int32_t* radii, const float* splats, const int32_t* tiles_per_gauss, int W, int H,
+                                 int legacy, int cam_id, int n_cams, long long capacity, int32_t* tile_counts,
+                                 const int32_t* tile_offsets, void* packed, int64_t* keys, int32_t* vals, adb_stream_t stream);
 int adb_raster_blend_fwd(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
                          const int32_t* tile_offsets, float* colors /*[H,W,4]*/, float* alphas /*[H,W]*/,
                          int32_t* last_ids /*[H,W]*/, adb_stream_t stream);
@@ -202,6 +217,9 @@ int adb_conv3x3_bf16(int B, int H, int W, int Cin, int Cout, const void* x_hi, c
 int adb_attention_bf16(int B, int heads, int Nq, int Nk, int Nkpad, const void* Q_hi, const void* Q_lo, const void* K_hi,
                        const void* K_lo, const void* Vt_hi, const void* Vt_lo, float scale, void* O_hi, void* O_lo,
                        adb_stream_t stream);
+/* Attention kernel choice: 0 = automatic by wave count (default), 1 = one 128-query tile per CTA, 2 = two query tiles per
+ * persistent CTA sharing every K/V block.  Returns the previous setting (-1: bad argument).  Diagnostic / test switch. */
+int adb_attention_set_variant(int variant);
 int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
                   void* y_hi, void* y_lo, adb_stream_t stream);
 int adb_split_bf16(long long n, const float* x, void* hi, void* lo, adb_stream_t stream);

@@ -1,11 +1,47 @@
-"""Drop-in for the matching half of the reference's ``mast3r_slam_backends`` extension (VSLAM/backend/src/gn.cpp:84-112):
-``iter_proj`` and ``refine_matches``.  The Gauss-Newton entry points (``gauss_newton_points / _rays / _calib``, SURVEY.md §8f
-rank 4) are outside this build's scope and raise."""
+"""Drop-in for the reference's ``mast3r_slam_backends`` extension (VSLAM/backend/src/gn.cpp:84-112).
+
+``iter_proj`` and ``refine_matches`` are served by artdeco_b200's kernels.  Every other attribute (the Gauss-Newton entry
+points ``gauss_newton_points / _rays / _calib`` that VSLAM/mast3r_slam/global_opt.py calls) is DELEGATED to the reference's own
+compiled extension when one is importable further down ``sys.path`` — putting ``shims/`` first must not take the SLAM
+pipeline's global optimisation away.  Only when no real extension exists does the lookup fail, loudly."""
+import importlib.machinery
+import importlib.util
+import os
+import sys
+
 from artdeco_b200.matching import iter_proj, refine_matches  # noqa: F401
+
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_real = None
+
+
+def _load_real():
+    """Finds a ``mast3r_slam_backends`` module on sys.path that is NOT this shim and imports it under a private name."""
+    global _real
+    if _real is not None:
+        return _real
+    paths = [p for p in sys.path if os.path.abspath(p or ".") != _HERE]
+    spec = importlib.machinery.PathFinder.find_spec("mast3r_slam_backends", paths)
+    if spec is None or spec.loader is None:
+        return None
+    spec.name = "_mast3r_slam_backends_real"
+    if hasattr(spec.loader, "name"):
+        # extension modules export PyInit_mast3r_slam_backends: keep the loader's name so the init symbol resolves
+        spec = importlib.util.spec_from_file_location("mast3r_slam_backends", spec.origin,
+                                                      submodule_search_locations=spec.submodule_search_locations)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _real = mod
+    return mod
 
 
 def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    real = _load_real()
+    if real is not None and hasattr(real, name):
+        return getattr(real, name)
     if name.startswith("gauss_newton"):
-        raise NotImplementedError(f"mast3r_slam_backends.{name}: the global Gauss-Newton solver is out of scope "
-                                  "(SURVEY.md §8f rank 4); only iter_proj / refine_matches are provided")
+        raise NotImplementedError(f"mast3r_slam_backends.{name}: artdeco_b200 serves iter_proj / refine_matches only and no "
+                                  "compiled reference extension was found on sys.path to delegate the Gauss-Newton solver to")
     raise AttributeError(name)

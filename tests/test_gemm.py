@@ -93,15 +93,23 @@ def test_layernorm_softmax_rope_im2col(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,h,Nq,Nk", [(1, 2, 128, 128), (2, 3, 200, 200), (1, 16, 1024, 1024), (2, 12, 768, 768), (1, 2, 12, 12), (1, 2, 300, 130)])
-def test_fused_attention_matches_fp64(cuda, B, h, Nq, Nk):
-    """csrc/attn_tc.cu against softmax(q k^T / 8) v in fp64 (blocks.py:105-109,162-166)."""
+@pytest.mark.parametrize("variant", [1, 2, 0], ids=["one_qtile_per_cta", "two_qtiles_persistent", "auto"])
+@pytest.mark.parametrize("B,h,Nq,Nk", [(1, 2, 128, 128), (2, 3, 200, 200), (1, 16, 1024, 1024), (2, 12, 768, 768), (1, 2, 12, 12), (1, 2, 300, 130),
+                                       (8, 16, 1024, 1024)])
+def test_fused_attention_matches_fp64(cuda, B, h, Nq, Nk, variant):
+    """csrc/attn_tc.cu (both kernel variants, and the automatic choice) against softmax(q k^T / 8) v in fp64
+    (blocks.py:105-109,162-166).  (8,16,1024,1024) is the encoder call of the B=4 bench: 512 persistent work items."""
     from artdeco_b200.mast3r import ops
     q, k, v = _mk((B, h, Nq, 64), 1, cuda), _mk((B, h, Nk, 64), 2, cuda), _mk((B, h, Nk, 64), 3, cuda)
     Nkpad = (Nk + 7) // 8 * 8
     vt = torch.zeros(B, h, 64, Nkpad, device=cuda)
     vt[..., :Nk] = v.transpose(-1, -2)
-    o = ops.attention(ops.split(q), ops.split(k), ops.split(vt), B, h, Nq, Nk, Nkpad, 0.125)
+    prev = ops.set_attention_variant(variant)
+    try:
+        o = ops.attention(ops.split(q), ops.split(k), ops.split(vt), B, h, Nq, Nk, Nkpad, 0.125)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_attention_variant(prev)
     ref = (torch.softmax(0.125 * q.double() @ k.double().transpose(-1, -2), -1) @ v.double()).permute(0, 2, 1, 3).reshape(B * Nq, h * 64)
     assert rel_err(o.hi.float() + o.lo.float(), ref) < 3e-5
 

@@ -23,13 +23,17 @@ def _tiny(N=80, W=48, H=32, seed=4):
 def _settings(V, K, W, H, bg, sh_degree=3, scale_modifier=1.0):
     from artdeco_b200.legacy import GaussianRasterizationSettings
     tanx, tany = W / (2 * float(K[0, 0])), H / (2 * float(K[1, 1]))
-    # symmetric frustum projection as Reconstruct/utils.py:154-178 builds it; the legacy API takes the transposes
+    # projection-only matrix as the reference's call site builds it (getProjectionMatrix2, Reconstruct/utils.py:133-154,
+    # passed transposed: webviewer/scene_models.py:549-566); the view matrix goes in per call, also transposed
+    fx, fy, cx, cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
     P = torch.zeros(4, 4)
     zn, zf = 0.01, 100.0
-    P[0, 0], P[1, 1], P[3, 2], P[2, 2], P[2, 3] = 1 / tanx, 1 / tany, 1.0, zf / (zf - zn), -(zf * zn) / (zf - zn)
-    full_t = (P @ V).t().contiguous()
+    P[0, 0], P[1, 1] = 2 * fx / W, 2 * fy / H
+    P[0, 2], P[1, 2] = (2 * cx - W) / W, (2 * cy - H) / H
+    P[3, 2], P[2, 2], P[2, 3] = 1.0, zf / (zf - zn), -(zf * zn) / (zf - zn)
     campos = torch.inverse(V)[:3, 3]
-    return GaussianRasterizationSettings(H, W, tanx, tany, bg, scale_modifier, full_t, sh_degree, campos, False, False)
+    return GaussianRasterizationSettings(H, W, tanx, tany, bg, scale_modifier, P.t().contiguous(), sh_degree, campos,
+                                         False, False)
 
 
 def test_oracle_legacy_properties():
@@ -96,3 +100,15 @@ def test_legacy_shim_import_surface(cuda):
                                    V.t().contiguous().to(cuda))
     assert torch.isfinite(color).all() and torch.isfinite(inv).all() and int((radii > 0).sum()) > 10000
     assert int(main.max()) < 50000 and int(main.min()) >= -1
+
+
+def test_intrinsics_come_from_the_projection_only_matrix():
+    """the legacy settings carry getProjectionMatrix2(...).T (projection only); the principal point must come
+    back exactly for an off-centre cx/cy whatever the pose is (host-side logic, no kernel)."""
+    from artdeco_b200.legacy import _intrinsics
+    W, H = 640, 480
+    K = torch.tensor([[500.0, 0, 300.0], [0, 480.0, 250.0], [0, 0, 1]])
+    V, _ = synthetic.camera(W, H, view=7.0)          # non-identity pose: must not matter
+    s = _settings(V, K, W, H, torch.zeros(3))
+    Kb = _intrinsics(s, torch.device("cpu"))
+    assert torch.allclose(Kb, K, atol=1e-4), Kb

@@ -96,6 +96,35 @@ def test_cuda_model_matches_reference_golden_full(cuda):
 
 
 @pytest.mark.gpu
+def test_graphed_b4_replay_matches_golden_and_eager(cuda):
+    """The configuration bench.py times: GraphedForwardPair(model, 4, 512, 512) on two streams, REPLAYED (the race fixed
+    in round 1 only showed under replay).  Batch item 0 is the golden pair, so all four outputs of both views are checked
+    against the real reference's outputs (mast3r_full.pt); every output of the graph must be bit-identical to the eager
+    forward_pair on the same batch, on the first and on the second replay (utils_mast3r.py:30-36 is the eager call)."""
+    from artdeco_b200.mast3r import AsymmetricMASt3R, GraphedForwardPair, forward_pair
+    g = _gold("full")
+    s, H, W = g["stride"], g["H"], g["W"]
+    sd = synthetic.det_weights(mt.param_shapes(g["cfg"]))
+    m = AsymmetricMASt3R(precision="bf16x3", **g["cfg"]).load_state_dict(sd).to(cuda)
+    a1, a2 = synthetic.mast3r_pair(1, H, W, seed=0)
+    r1, r2 = synthetic.mast3r_pair(3, H, W, seed=21)
+    i1, i2 = torch.cat((a1, r1)).to(cuda), torch.cat((a2, r2)).to(cuda)
+    e1, e2 = forward_pair(m, i1, i2)
+    e1 = {k: v.clone() for k, v in e1.items()}
+    e2 = {k: v.clone() for k, v in e2.items()}
+    graphed = GraphedForwardPair(m, 4, H, W)
+    for replay in range(2):
+        if replay == 1:      # a different batch in between, so that replay 2 cannot pass on stale buffers
+            graphed(i2, i1)
+        o1, o2 = graphed(i1, i2)
+        torch.cuda.synchronize()
+        for k in KEYS:
+            assert rel_err(o1[k][:1, ::s, ::s], g["h1." + k]) < 1e-4, f"replay {replay} head1 {k} vs reference golden"
+            assert rel_err(o2[k][:1, ::s, ::s], g["h2." + k]) < 1e-4, f"replay {replay} head2 {k} vs reference golden"
+            assert torch.equal(o1[k], e1[k]) and torch.equal(o2[k], e2[k]), f"replay {replay}: graph != eager ({k})"
+
+
+@pytest.mark.gpu
 def test_cuda_model_vs_oracle_odd_shape_and_batch(cuda):
     """512x384-style aspect (PINGPONG's real shape, scaled down) and batch 2, against the oracle run on the GPU in fp32."""
     cfg, H, W = mt.SMALL_CFG, 96, 128

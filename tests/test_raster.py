@@ -105,6 +105,45 @@ def test_backward_matches_oracle(cuda, N, W, H):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N,view", [(100_000, 0.0), (1_000_000, 3.5)], ids=["config2_100k_1080p", "headline_1M_1080p"])
+def test_baseline_configs_fwd_bwd_match_oracle(cuda, N, view):
+    """BASELINE.json configs[1] (100k Gaussians, 1080p) and the headline workload (1M, 1080p, view 3.5 -- exactly what
+    bench.py times): forward AND backward against the C oracle on the same seeded inputs, through the public
+    rasterization() + autograd.  Keys / sort indices / offsets / radii bit-exact; image and every gradient within 1e-4
+    of scale.  (The oracle needs ~2 s per fwd+bwd at 1M on the GPU box's host cores.)"""
+    from artdeco_b200 import raster as R
+    W, H = 1920, 1080
+    sc, V, K = _scene(N, W, H, seed=0, view=view)
+    args = [sc[k].numpy() for k in KEYS]
+    f = oracle.rasterize_fwd(*args, V.numpy(), K.numpy(), W, H)
+    vc, va = synthetic.upstream_grads(W, H, seed=1)
+    b = oracle.rasterize_bwd(*args, V.numpy(), f, vc[0].numpy(), va[0, ..., 0].numpy())
+
+    t = {k: sc[k].to(cuda).requires_grad_(True) for k in KEYS}
+    Vd = V.to(cuda).requires_grad_(True)
+    colors, alphas, meta = R.rasterization(t["means"], t["quats"], t["scales"], t["opacities"], t["sh"], Vd[None],
+                                           K.to(cuda)[None], W, H, render_mode="RGB+D", sh_degree=3, eps2d=0.01)
+    assert np.array_equal(meta["radii"][0].cpu().numpy(), f["radii"]), "radii"
+    assert np.array_equal(meta["isect_ids"].cpu().numpy(), f["keys"]), "sorted tile keys"
+    assert np.array_equal(meta["flatten_ids"].cpu().numpy(), f["vals"]), "sort indices"
+    assert np.array_equal(meta["isect_offsets"].reshape(-1).cpu().numpy(), f["tile_offsets"]), "tile offsets"
+    assert_close(colors[0], f["colors"], what="colors", max_outlier_frac=1e-4)
+    assert_close(alphas[0, ..., 0], f["alphas"], what="alphas", max_outlier_frac=1e-4)
+    ((colors * vc.to(cuda)).sum() + (alphas * va.to(cuda)).sum()).backward()
+    fr = 2e-4
+    assert_close(t["means"].grad, b["v_means"], what="v_means", max_outlier_frac=fr)
+    assert_close(t["quats"].grad, b["v_quats"], what="v_quats", max_outlier_frac=fr)
+    assert_close(t["scales"].grad, b["v_scales"], what="v_scales", max_outlier_frac=fr)
+    assert_close(t["opacities"].grad, b["v_opac"], what="v_opac", max_outlier_frac=fr)
+    assert_close(t["sh"].grad, b["v_sh"], what="v_sh", max_outlier_frac=fr)
+    Vt = V.double().requires_grad_(True)
+    (torch.inverse(Vt)[:3, 3] * torch.tensor(b["v_campos"], dtype=torch.float64)).sum().backward()
+    vV = b["v_viewmat"].astype(np.float64) + Vt.grad.numpy()
+    # a sum over up to 1M Gaussians in fp32 on both sides (different orders): 1e-3 of scale
+    assert rel_err(Vd.grad.cpu().numpy()[:3], vV[:3]) < 1e-3, "viewmat gradient"
+
+
+@pytest.mark.gpu
 def test_edge_cases(cuda):
     from artdeco_b200 import raster as R
     V, K = synthetic.camera(70, 50, focal=50.0)  # ragged: not a multiple of 16

@@ -47,6 +47,21 @@ def test_shims_expose_the_reference_names(shims_on_path):
     assert s.image_height == 4 and s.image_width == 6 and s.sh_degree == 3      # positional order of webviewer/scene_models.py:559-571
 
 
+def test_backend_shim_delegates_gauss_newton_to_a_real_extension(shims_on_path, tmp_path):
+    """with shims/ first on sys.path the Gauss-Newton entry points must still reach the reference's compiled
+    extension further down the path (here: a stand-in module)."""
+    (tmp_path / "mast3r_slam_backends.py").write_text("def gauss_newton_rays(*a):\n    return ('real', len(a))\n")
+    sys.path.append(str(tmp_path))
+    try:
+        sys.modules.pop("mast3r_slam_backends", None)
+        b = importlib.import_module("mast3r_slam_backends")
+        assert b.gauss_newton_rays(1, 2, 3) == ("real", 3)
+        assert b.iter_proj.__module__.startswith("artdeco_b200")       # ours still wins for the matching half
+    finally:
+        sys.path.remove(str(tmp_path))
+        sys.modules.pop("mast3r_slam_backends", None)
+
+
 def test_every_operator_family_fails_loudly_on_cpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
