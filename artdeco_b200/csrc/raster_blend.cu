@@ -58,8 +58,10 @@ struct WarpRect {
 
 // Shared-memory record (3 x float4, 48 B stride: conflict-free for both the staging stores and the broadcast loads):
 //   A = (mx, my, ha, b2)   B = (hc, opacity, smax2, bits rx|ry<<16)   C = (r, g, b, depth | 1/depth for LEGACY)
-// with ha = log2e * a/2, b2 = log2e * b, hc = log2e * c/2, smax2 = log2e * (ln(255 o) + margin):
-//   sigma2 = log2e * sigma = dx (ha dx + b2 dy) + hc dy^2,   alpha = o * 2^(-sigma2).
+// with ha = log2e * a/2, b2 = log2e * b, hc = log2e * c/2, smax2 = log2e * ln(255 o) (the projection's margin removed):
+//   sigma2 = log2e * sigma = dx (ha dx + b2 dy) + hc dy^2,   alpha = o * 2^(-sigma2),
+//   and  alpha >= 1/255  <=>  sigma2 <= smax2  — one compare replaces the alpha test (the two differ only where
+//   o 2^(-sigma2) is within an ulp of 1/255, the same measure-zero band in which ex2.approx and the oracle's expf disagree).
 template <bool LEGACY>
 __device__ __forceinline__ void stage_record(float4* __restrict__ rec, const float* __restrict__ splats, int g) {
     const float4* p = reinterpret_cast<const float4*>(splats + (size_t)g * ADB_SPLAT_STRIDE);
@@ -67,7 +69,7 @@ __device__ __forceinline__ void stage_record(float4* __restrict__ rec, const flo
     A.z *= 0.5f * LOG2E;
     A.w *= LOG2E;
     B.x *= 0.5f * LOG2E;
-    B.z *= LOG2E;
+    B.z = (B.z - ADB_SIGMA_MARGIN) * LOG2E;   // exact bound: alpha >= 1/255  <=>  sigma <= ln(255 o)
     if (LEGACY) C.w = 1.0f / C.w;   // Inria: 4th channel blends 1/z (v_splats slot 9 is then dL/d(1/z))
     rec[0] = A;
     rec[1] = B;
@@ -185,7 +187,7 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
                 const float dx = A.x - px, dy = A.y - py;
                 const float s2 = dx * (A.z * dx + A.w * dy) + (B.x * dy) * dy;
                 const float alpha = fminf(MAXA, B.y * ex2_approx(-s2));
-                const bool ok = !done && s2 >= 0.f && s2 <= B.z && alpha >= ADB_ALPHA_THRESHOLD;
+                const bool ok = !done && s2 >= 0.f && s2 <= B.z;
                 const float nT = fmaf(-T, alpha, T);
                 const bool stop = ok && (LEGACY ? (nT < ADB_T_EPS) : (nT <= ADB_T_EPS));
                 const bool take = ok && !stop;
@@ -232,8 +234,8 @@ struct BwdSmem {
     static_assert(OFF_G % 16 == 0 && OFF_LIST % 16 == 0 && OFF_VO % 16 == 0 && OFF_V % 16 == 0, "alignment");
 };
 
-template <bool LEGACY, int S>
-__global__ void __launch_bounds__(BLOCK, 3)
+template <bool LEGACY, int S, int OCC>
+__global__ void __launch_bounds__(BLOCK, OCC)
 blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* __restrict__ vals,
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
                  const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
@@ -314,7 +316,7 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
                     const float s2 = dx * (A.z * dx + A.w * dy) + (B.x * dy) * dy;
                     const float ov = B.y * ex2_approx(-s2);
                     const float am = fminf(MAXA, ov);
-                    const bool valid = t >= tmin && s2 >= 0.f && s2 <= B.z && am >= ADB_ALPHA_THRESHOLD;
+                    const bool valid = t >= tmin && s2 >= 0.f && s2 <= B.z;
                     // An invalid lane runs with alpha = 0, which leaves T and bv unchanged (ra = 1, fac = 0) and
                     // contributes exact zeros to every sum.
                     const float alpha = valid ? am : 0.f;
@@ -424,18 +426,18 @@ ADB_API int adb_raster_blend_fwd_legacy(int W, int H, int n_per_cam, const float
                           stream);
 }
 
-template <bool LEGACY, int S>
+template <bool LEGACY, int S, int OCC>
 static int launch_bwd(dim3 grid, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
                       const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids, const float* v_colors,
                       const float* v_alphas, float* v_splats, cudaStream_t stream) {
     static AdbDeviceOnce once;
     const int rc = once.ensure([]() -> int {
-        ADB_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<LEGACY, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ADB_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<LEGACY, S, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       BwdSmem<S>::BYTES));
         return ADB_OK;
     });
     if (rc != ADB_OK) return rc;
-    blend_bwd_kernel<LEGACY, S><<<grid, BLOCK, BwdSmem<S>::BYTES, stream>>>(
+    blend_bwd_kernel<LEGACY, S, OCC><<<grid, BLOCK, BwdSmem<S>::BYTES, stream>>>(
         W, H, splats, vals_sorted, tile_offsets, n_per_cam, alphas, last_ids, v_colors, v_alphas, v_splats);
     return ADB_OK;
 }
@@ -448,18 +450,17 @@ static int blend_bwd_impl(bool legacy, int W, int H, int n_per_cam, const float*
     if (n_per_cam == 0) return ADB_OK;
     ADB_REQUIRE(v_splats, "adb_raster_blend_bwd: null v_splats");
     dim3 grid(adb_cdiv(W, ADB_TILE), adb_cdiv(H, ADB_TILE));
-    // ADB_BWD_SLOTS=32: 32-slot deferred-reduction buffer (A/B switch; 16 keeps 3 CTAs per SM)
+    // A/B switches: ADB_BWD_SLOTS=32 -> 32-slot deferred-reduction buffer (2 CTAs/SM; measured 0.75 vs 0.64 ms);
+    // ADB_BWD_OCC=3 -> 79 registers, 3 CTAs/SM instead of the default 64 registers, 4 CTAs/SM (12 B of spills; 0.630 vs 0.640 ms).
     static const int slots = getenv("ADB_BWD_SLOTS") ? atoi(getenv("ADB_BWD_SLOTS")) : 16;
+    static const int occ = getenv("ADB_BWD_OCC") ? atoi(getenv("ADB_BWD_OCC")) : 4;
     int rc;
-    if (legacy)
-        rc = launch_bwd<true, 16>(grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
-                                  v_alphas, v_splats, stream);
-    else if (slots == 32)
-        rc = launch_bwd<false, 32>(grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
-                                   v_alphas, v_splats, stream);
-    else
-        rc = launch_bwd<false, 16>(grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
-                                   v_alphas, v_splats, stream);
+#define ADB_BWD_ARGS grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors, v_alphas, v_splats, stream
+    if (legacy) rc = launch_bwd<true, 16, 3>(ADB_BWD_ARGS);
+    else if (slots == 32) rc = launch_bwd<false, 32, 2>(ADB_BWD_ARGS);
+    else if (occ == 4) rc = launch_bwd<false, 16, 4>(ADB_BWD_ARGS);
+    else rc = launch_bwd<false, 16, 3>(ADB_BWD_ARGS);
+#undef ADB_BWD_ARGS
     if (rc != ADB_OK) return rc;
     ADB_CHECK_LAUNCH("blend_bwd_kernel");
     return ADB_OK;

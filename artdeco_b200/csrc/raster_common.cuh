@@ -22,6 +22,8 @@
 #define ADB_ALPHA_THRESHOLD (1.0f / 255.0f)
 #define ADB_MAX_ALPHA 0.999f
 #define ADB_T_EPS 1e-4f
+#define ADB_TILE_COUNTER_COPIES 4   // replicas of every tile counter in the bucketed intersection (raster_isect.cu)
+#define ADB_SIGMA_MARGIN 0.02f   // splat record slot 6 = ln(255*opacity) + this (raster_project.cu)
 // Rendering conventions.  GSPLAT: what the live path uses (h3dgsv3.py:664-680).  INRIA: the legacy
 // diff_gaussian_rasterization contract of the web viewer (Reconstruct/webviewer/scene_models.py:559-605):
 // radius ceil(3 sqrt(lambda_max)) with a 0.1 floor under the root, tile rectangle on pixel-index coordinates

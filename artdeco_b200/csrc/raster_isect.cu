@@ -162,13 +162,18 @@ ADB_API int adb_raster_tile_offsets(long long n_isect, const int64_t* keys_sorte
 // =====================================================================================================================
 // Tile-bucketed intersection (round 2): no library sort, no host sync, bit-identical output.
 //
-//   count    per Gaussian: one RED.ADD per touched tile into tile_counts[T]                (integer, 16 B read / Gaussian)
-//   scan     one CTA: exclusive scan of tile_counts -> tile_offsets[T+1] (clamped to the caller's capacity; total and
-//            overflow flag stay on the device)
-//   scatter  per Gaussian: slot = offsets[tile] + atomicSub(counts[tile]) - 1 -> packed[slot] = depth_bits<<32 | gaussian
-//            (arbitrary order inside a tile; the counters return to zero, so the buffer needs no memset between calls)
-//   sort     one CTA per tile: bitonic sort of the tile's 64-bit words in shared memory (in place in global memory for
-//            tiles beyond 4096 entries), then keys = cam|tile|depth_bits and vals = cam*N + gaussian are written out.
+//   count    per Gaussian: one RED.ADD per touched tile into tile_counts[tile][copy]            (16 B read / Gaussian)
+//   scan     one CTA: exclusive scan of the T x COPIES counters -> per-(tile,copy) segment starts + tile_offsets[T+1]
+//            (clamped to the caller's capacity; the true total and an overflow flag stay on the device)
+//   scatter  per Gaussian: slot = start[tile][copy] + atomicSub(counter) - 1 -> packed[slot] = depth_bits<<32 | gaussian
+//            (arbitrary order inside a tile; the counters return to zero, so the buffer needs no memset between calls;
+//            four atomics are in flight per thread before the first dependent store)
+//   sort     one CTA per tile: bitonic sort of the tile's 64-bit words — the 64-element sub-networks run in REGISTERS with
+//            warp shuffles, only the wider exchanges go through shared memory (global memory for tiles beyond 4096
+//            entries) — then keys = cam|tile|depth_bits and vals = cam*N + gaussian are written out.
+//
+// COPIES = 4 replicas of every tile counter (selected by CTA index) cut the same-address serialisation of the L2 atomics:
+// with one counter per tile the count kernel ran at 45 G atomics/s (profiles/r02_summary.md).
 //
 // Why the order equals the reference's stable radix sort of (tile, depth): the reference emits keys Gaussian-major, so
 // inside one (tile, depth) tie the stable sort leaves ascending Gaussian ids — exactly the ascending order of the
@@ -176,6 +181,8 @@ ADB_API int adb_raster_tile_offsets(long long n_isect, const int64_t* keys_sorte
 // and the result does not depend on the scatter order.  (oracle: adbo_isect_sort.)
 // The global 45-bit onesweep radix sort this replaces moved 6 x 24 B per intersection and was 12.6 % of the round-1 step.
 namespace {
+
+constexpr int COPIES = ADB_TILE_COUNTER_COPIES;
 
 __global__ void __launch_bounds__(256)
 tile_count_kernel(int N, const int32_t* __restrict__ radii, const float* __restrict__ splats,
@@ -187,24 +194,34 @@ tile_count_kernel(int N, const int32_t* __restrict__ radii, const float* __restr
     const int2 r = reinterpret_cast<const int2*>(radii)[i];
     const float2 m = reinterpret_cast<const float2*>(splats + (size_t)i * ADB_SPLAT_STRIDE)[0];
     const int tw = (W + ADB_TILE - 1) / ADB_TILE;
+    const int cp = blockIdx.x & (COPIES - 1);
     int x0, x1, y0, y1;
     adb_tile_rect(m.x, m.y, r.x, r.y, W, H, convention, x0, x1, y0, y1);
     for (int ty = y0; ty < y1; ++ty)
-        for (int tx = x0; tx < x1; ++tx) atomicAdd(tile_counts + ty * tw + tx, 1);
+        for (int tx = x0; tx < x1; ++tx) atomicAdd(tile_counts + (ty * tw + tx) * COPIES + cp, 1);
 }
 
-// Single CTA, 1024 threads.  offsets[t] = min(capacity, sum_{u<t} counts[u]); offsets[T] likewise; *total = unclamped sum.
+// Single CTA, 1024 threads, over the T*COPIES counters in (tile-major, copy-minor) order.
+// starts[e] = min(capacity, sum_{f<e} counts[f]);  offsets[t] = starts[t*COPIES];  offsets[T] = min(capacity, total).
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(int T, const int32_t* __restrict__ counts, long long capacity, int32_t* __restrict__ offsets,
-                 long long* __restrict__ total, int32_t* __restrict__ overflow) {
+tile_scan_kernel(int T, const int32_t* __restrict__ counts, long long capacity, int32_t* __restrict__ starts,
+                 int32_t* __restrict__ offsets, long long* __restrict__ total, int32_t* __restrict__ overflow) {
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = T * COPIES;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + tid;
-        const long long c = t < T ? (long long)counts[t] : 0;
+    for (int base = 0; base < E; base += 1024 * 4) {
+        const int e0 = base + tid * 4;                      // 4 consecutive counters (= one tile's copies) per thread
+        int4 c4 = make_int4(0, 0, 0, 0);
+        if (e0 + 3 < E) c4 = *reinterpret_cast<const int4*>(counts + e0);
+        else {
+            if (e0 < E) c4.x = counts[e0];
+            if (e0 + 1 < E) c4.y = counts[e0 + 1];
+            if (e0 + 2 < E) c4.z = counts[e0 + 2];
+        }
+        const long long c = (long long)c4.x + c4.y + c4.z + c4.w;
         long long x = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -224,8 +241,18 @@ tile_scan_kernel(int T, const int32_t* __restrict__ counts, long long capacity, 
         }
         __syncthreads();
         const long long carry = s_carry;
-        const long long excl = carry + (warp ? s_warp[warp - 1] : 0) + x - c;
-        if (t < T) offsets[t] = (int32_t)(excl < capacity ? excl : capacity);
+        long long excl = carry + (warp ? s_warp[warp - 1] : 0) + x - c;
+        const long long cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u;
+            if (e < E) {
+                const int32_t v = (int32_t)(excl < capacity ? excl : capacity);
+                starts[e] = v;
+                if ((e & (COPIES - 1)) == 0) offsets[e / COPIES] = v;
+            }
+            excl += cc[u];
+        }
         __syncthreads();
         if (tid == 1023) s_carry = carry + s_warp[31];
         __syncthreads();
@@ -241,7 +268,7 @@ tile_scan_kernel(int T, const int32_t* __restrict__ counts, long long capacity, 
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(int N, const int32_t* __restrict__ radii, const float* __restrict__ splats,
                     const int32_t* __restrict__ tiles_per_gauss, int W, int H, int convention,
-                    const int32_t* __restrict__ offsets, int32_t* __restrict__ tile_counts, long long capacity,
+                    const int32_t* __restrict__ starts, int32_t* __restrict__ tile_counts, long long capacity,
                     unsigned long long* __restrict__ packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -250,44 +277,152 @@ tile_scatter_kernel(int N, const int32_t* __restrict__ radii, const float* __res
     const float2 m = reinterpret_cast<const float2*>(splats + (size_t)i * ADB_SPLAT_STRIDE)[0];
     const float depth = splats[(size_t)i * ADB_SPLAT_STRIDE + 11];
     const int tw = (W + ADB_TILE - 1) / ADB_TILE;
+    const int cp = blockIdx.x & (COPIES - 1);
     int x0, x1, y0, y1;
     adb_tile_rect(m.x, m.y, r.x, r.y, W, H, convention, x0, x1, y0, y1);
     const unsigned long long word = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned)i;
-    for (int ty = y0; ty < y1; ++ty)
-        for (int tx = x0; tx < x1; ++tx) {
-            const int t = ty * tw + tx;
-            const long long slot = (long long)offsets[t] + (atomicSub(tile_counts + t, 1) - 1);
-            if (slot < capacity) packed[slot] = word;
+    int tx = x0, ty = y0;
+    while (ty < y1) {
+        int e[4], a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                       // up to four atomics in flight
+            e[u] = -1;
+            if (ty < y1) {
+                e[u] = (ty * tw + tx) * COPIES + cp;
+                a[u] = atomicSub(tile_counts + e[u], 1);
+                if (++tx == x1) { tx = x0; ++ty; }
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (e[u] >= 0) {
+                const long long slot = (long long)starts[e[u]] + (a[u] - 1);
+                if (slot < capacity) packed[slot] = word;
+            }
+    }
 }
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_SMEM_CAP = 4096;    // words sorted in shared memory (32 KB); larger tiles sort in place in global memory
+typedef unsigned long long u64;
 
-// All compare-exchanges ascending ("flip" then "disperse" steps), so indices >= n behave as +inf and are simply skipped:
-// any n works without padding.
-template <class Ptr>
-__device__ __forceinline__ void bitonic_sort_words(Ptr a, int n, int tid, int nthreads) {
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    const int pairs = np2 >> 1;
-    for (int k = 2; k <= np2; k <<= 1) {
-        const int h = k >> 1;
-        for (int q = tid; q < pairs; q += nthreads) {                  // flip: i <-> block_end - 1 - (i - block_start)
-            const int blk = q / h, r = q - blk * h;
-            const int i = blk * k + r, p = blk * k + (k - 1 - r);
+__device__ __forceinline__ void ce_keep(u64& mine, u64 other, bool keep_min) {
+    const bool lt = other < mine;
+    mine = (lt == keep_min) ? other : mine;
+}
+
+// Bitonic network on one 64-element chunk held by a warp: lane holds positions `lane` (e0) and `lane + 32` (e1).
+// Runs the merge levels [lk_first .. 6] when `full`, else only the disperse steps j = 32..1 (tail of a wider merge).
+__device__ __forceinline__ void chunk_network(u64& e0, u64& e1, int lane, bool full) {
+    if (full) {
+#pragma unroll
+        for (int lk = 1; lk <= 5; ++lk) {                   // blocks of k = 2^lk <= 32: both halves independently
+            const int k = 1 << lk;
+            {   // flip: p <-> p ^ (k-1); the lower position keeps the minimum
+                const bool low = (lane & (k >> 1)) == 0;
+                const u64 y0 = __shfl_xor_sync(0xffffffffu, e0, k - 1), y1 = __shfl_xor_sync(0xffffffffu, e1, k - 1);
+                ce_keep(e0, y0, low);
+                ce_keep(e1, y1, low);
+            }
+#pragma unroll
+            for (int j = k >> 2; j > 0; j >>= 1) {          // disperse: p <-> p ^ j
+                const bool low = (lane & j) == 0;
+                const u64 y0 = __shfl_xor_sync(0xffffffffu, e0, j), y1 = __shfl_xor_sync(0xffffffffu, e1, j);
+                ce_keep(e0, y0, low);
+                ce_keep(e1, y1, low);
+            }
+        }
+        {   // k = 64 flip: position p (e0 of lane p) <-> 63 - p (e1 of lane 31 - p)
+            const u64 y = __shfl_sync(0xffffffffu, e1, 31 - lane), z = __shfl_sync(0xffffffffu, e0, 31 - lane);
+            ce_keep(e0, y, true);
+            ce_keep(e1, z, false);
+        }
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const bool low = (lane & j) == 0;
+            const u64 y0 = __shfl_xor_sync(0xffffffffu, e0, j), y1 = __shfl_xor_sync(0xffffffffu, e1, j);
+            ce_keep(e0, y0, low);
+            ce_keep(e1, y1, low);
+        }
+    } else {
+        {   // j = 32: positions lane and lane + 32 live in the same lane
+            const u64 lo = e0 < e1 ? e0 : e1, hi = e0 < e1 ? e1 : e0;
+            e0 = lo; e1 = hi;
+        }
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const bool low = (lane & j) == 0;
+            const u64 y0 = __shfl_xor_sync(0xffffffffu, e0, j), y1 = __shfl_xor_sync(0xffffffffu, e1, j);
+            ce_keep(e0, y0, low);
+            ce_keep(e1, y1, low);
+        }
+    }
+}
+
+// Sorts a[0..np2) ascending (np2 a power of two >= 64, padded with ~0 by the caller).  All compare-exchanges ascending
+// ("flip" then "disperse" steps).  Exchanges at distance >= 64 go through `a` (shared memory); everything inside aligned
+// 64-element chunks runs in registers.
+__device__ __forceinline__ void bitonic_sort_shared(u64* a, int np2, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, nwarp = SORT_THREADS / 32;
+    const int nchunk = np2 >> 6, pairs = np2 >> 1;
+    for (int c = warp; c < nchunk; c += nwarp) {            // levels k = 2..64 of every chunk
+        u64 e0 = a[c * 64 + lane], e1 = a[c * 64 + 32 + lane];
+        chunk_network(e0, e1, lane, true);
+        a[c * 64 + lane] = e0; a[c * 64 + 32 + lane] = e1;
+    }
+    __syncthreads();
+    for (int lk = 7; (1 << lk) <= np2; ++lk) {
+        const int lh = lk - 1, h = 1 << lh, k = 1 << lk;
+        for (int q = tid; q < pairs; q += SORT_THREADS) {  // flip across the block of k
+            const int r = q & (h - 1), base = (q >> lh) << lk;
+            const int i = base + r, p = base + (k - 1 - r);
+            const u64 x = a[i], y = a[p];
+            if (x > y) { a[i] = y; a[p] = x; }
+        }
+        __syncthreads();
+        for (int lj = lh - 1; lj >= 6; --lj) {              // disperse at distance j >= 64
+            const int j = 1 << lj;
+            for (int q = tid; q < pairs; q += SORT_THREADS) {
+                const int r = q & (j - 1);
+                const int i = ((q >> lj) << (lj + 1)) + r, p = i + j;
+                const u64 x = a[i], y = a[p];
+                if (x > y) { a[i] = y; a[p] = x; }
+            }
+            __syncthreads();
+        }
+        for (int c = warp; c < nchunk; c += nwarp) {        // disperse j = 32..1 inside every chunk
+            u64 e0 = a[c * 64 + lane], e1 = a[c * 64 + 32 + lane];
+            chunk_network(e0, e1, lane, false);
+            a[c * 64 + lane] = e0; a[c * 64 + 32 + lane] = e1;
+        }
+        __syncthreads();
+    }
+}
+
+// Fallback for tiles beyond the shared-memory capacity: same network, operands in global memory, any n (indices >= n
+// behave as +inf and are skipped).
+__device__ __forceinline__ void bitonic_sort_global(volatile u64* a, int n, int tid) {
+    int lg = 0;
+    while ((1 << lg) < n) ++lg;
+    const int pairs = (1 << lg) >> 1;
+    for (int lk = 1; lk <= lg; ++lk) {
+        const int lh = lk - 1, h = 1 << lh, k = 1 << lk;
+        for (int q = tid; q < pairs; q += SORT_THREADS) {
+            const int r = q & (h - 1), base = (q >> lh) << lk;
+            const int i = base + r, p = base + (k - 1 - r);
             if (p < n) {
-                const unsigned long long x = a[i], y = a[p];
+                const u64 x = a[i], y = a[p];
                 if (x > y) { a[i] = y; a[p] = x; }
             }
         }
         __syncthreads();
-        for (int j = h >> 1; j > 0; j >>= 1) {                          // disperse: i <-> i + j
-            for (int q = tid; q < pairs; q += nthreads) {
-                const int blk = q / j, r = q - blk * j;
-                const int i = blk * 2 * j + r, p = i + j;
+        for (int lj = lh - 1; lj >= 0; --lj) {
+            const int j = 1 << lj;
+            for (int q = tid; q < pairs; q += SORT_THREADS) {
+                const int r = q & (j - 1);
+                const int i = ((q >> lj) << (lj + 1)) + r, p = i + j;
                 if (p < n) {
-                    const unsigned long long x = a[i], y = a[p];
+                    const u64 x = a[i], y = a[p];
                     if (x > y) { a[i] = y; a[p] = x; }
                 }
             }
@@ -297,32 +432,34 @@ __device__ __forceinline__ void bitonic_sort_words(Ptr a, int n, int tid, int nt
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
-tile_sort_kernel(int T, const int32_t* __restrict__ offsets, unsigned long long* __restrict__ packed, int cam_id,
+tile_sort_kernel(int T, const int32_t* __restrict__ offsets, u64* __restrict__ packed, int cam_id,
                  int n_per_cam, int tile_bits, int64_t* __restrict__ keys, int32_t* __restrict__ vals) {
-    __shared__ unsigned long long s_words[SORT_SMEM_CAP];
+    __shared__ u64 s_words[SORT_SMEM_CAP];
     const int tile = blockIdx.x;
     const int start = offsets[tile], n = offsets[tile + 1] - start;
     if (n <= 0) return;
     const int tid = threadIdx.x;
-    unsigned long long* g = packed + start;
-    const unsigned long long hi = ((unsigned long long)cam_id << (32 + tile_bits)) | ((unsigned long long)tile << 32);
+    u64* g = packed + start;
+    const u64 hi = ((u64)cam_id << (32 + tile_bits)) | ((u64)tile << 32);
     const int vbase = cam_id * n_per_cam;
     if (n <= SORT_SMEM_CAP) {
-        for (int i = tid; i < n; i += SORT_THREADS) s_words[i] = g[i];
+        int np2 = 64;
+        while (np2 < n) np2 <<= 1;
+        for (int i = tid; i < np2; i += SORT_THREADS) s_words[i] = i < n ? g[i] : ~0ull;
         __syncthreads();
-        if (n > 1) bitonic_sort_words(s_words, n, tid, SORT_THREADS);
+        if (n > 1) bitonic_sort_shared(s_words, np2, tid);
         for (int i = tid; i < n; i += SORT_THREADS) {
-            const unsigned long long w = s_words[i];
+            const u64 w = s_words[i];
             keys[start + i] = (int64_t)(hi | (w >> 32));
             vals[start + i] = vbase + (int32_t)(unsigned)(w & 0xffffffffu);
         }
     } else {
-        // rare: a tile with more than SORT_SMEM_CAP splats.  Same network, operands in global memory (L2-resident).
+        // rare: a tile with more than SORT_SMEM_CAP splats (L2-resident operands)
         __syncthreads();
-        bitonic_sort_words((volatile unsigned long long*)g, n, tid, SORT_THREADS);
+        bitonic_sort_global((volatile u64*)g, n, tid);
         __threadfence_block();
         for (int i = tid; i < n; i += SORT_THREADS) {
-            const unsigned long long w = g[i];
+            const u64 w = g[i];
             keys[start + i] = (int64_t)(hi | (w >> 32));
             vals[start + i] = vbase + (int32_t)(unsigned)(w & 0xffffffffu);
         }
@@ -331,9 +468,11 @@ tile_sort_kernel(int T, const int32_t* __restrict__ offsets, unsigned long long*
 
 }  // namespace
 
-// tile_counts [T] int32 must be all-zero on entry (it is zero again after adb_raster_tile_scatter: allocate + zero once).
-// offsets [T+1]; total (int64, device) and overflow (int32, device, only ever SET) may be null.  `capacity` = number of
-// elements `packed`, `keys` and `vals` can hold; intersections beyond it are dropped (memory-safe) and flagged.
+// tile_counts: int32 [2 * ADB_TILE_COUNTER_COPIES * T]: first half = the per-(tile,copy) counters, which must be all-zero
+// on entry (they are zero again after adb_raster_tile_scatter_sort: allocate + zero once); second half = segment starts
+// written by the scan.  tile_offsets [T+1]; total (int64, device) and overflow (int32, device, only ever SET) may be null.
+// `capacity` = number of elements `packed`, `keys` and `vals` can hold; intersections beyond it are dropped (memory-safe)
+// and flagged.
 static int tile_bucket_impl(int convention, int N, const int32_t* radii, const float* splats,
                             const int32_t* tiles_per_gauss, int W, int H, long long capacity, int32_t* tile_counts,
                             int32_t* tile_offsets, long long* total, int32_t* overflow, cudaStream_t stream) {
@@ -346,7 +485,8 @@ static int tile_bucket_impl(int convention, int N, const int32_t* radii, const f
                                                                tile_counts);
         ADB_CHECK_LAUNCH("tile_count_kernel");
     }
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(T, tile_counts, capacity, tile_offsets, total, overflow);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(T, tile_counts, capacity, tile_counts + (size_t)T * COPIES, tile_offsets, total,
+                                            overflow);
     ADB_CHECK_LAUNCH("tile_scan_kernel");
     return ADB_OK;
 }
@@ -358,7 +498,8 @@ ADB_API int adb_raster_tile_count_scan(int N, const int32_t* radii, const float*
                             tile_counts, tile_offsets, total, overflow, stream);
 }
 
-// Scatter + per-tile sort.  keys [capacity] int64, vals [capacity] int32, packed [capacity] uint64 scratch.
+// Scatter + per-tile sort.  keys [capacity] int64, vals [capacity] int32, packed [capacity] uint64 scratch; tile_counts as
+// left by adb_raster_tile_count_scan.
 ADB_API int adb_raster_tile_scatter_sort(int N, const int32_t* radii, const float* splats, const int32_t* tiles_per_gauss,
                                          int W, int H, int legacy, int cam_id, int n_cams, long long capacity,
                                          int32_t* tile_counts, const int32_t* tile_offsets, void* packed, int64_t* keys,
@@ -370,8 +511,9 @@ ADB_API int adb_raster_tile_scatter_sort(int N, const int32_t* radii, const floa
                 "adb_raster_tile_scatter_sort: null pointer");
     const int T = adb_cdiv(W, ADB_TILE) * adb_cdiv(H, ADB_TILE);
     tile_scatter_kernel<<<adb_cdiv(N, 256), 256, 0, stream>>>(N, radii, splats, tiles_per_gauss, W, H,
-                                                             legacy ? ADB_CONV_INRIA : ADB_CONV_GSPLAT, tile_offsets,
-                                                             tile_counts, capacity, (unsigned long long*)packed);
+                                                             legacy ? ADB_CONV_INRIA : ADB_CONV_GSPLAT,
+                                                             tile_counts + (size_t)T * COPIES, tile_counts, capacity,
+                                                             (unsigned long long*)packed);
     ADB_CHECK_LAUNCH("tile_scatter_kernel");
     tile_sort_kernel<<<T, SORT_THREADS, 0, stream>>>(T, tile_offsets, (unsigned long long*)packed, cam_id, N,
                                                     adb_tile_bits(W, H), keys, vals);

@@ -275,6 +275,94 @@ inline int grid_for(long long n) { long long g = (n + 255) / 256; return (int)(g
 
 }  // namespace
 
+// ---- DPT head companions (round 2): the last eager PyTorch ops of the head ------------------------------------------
+// Bilinear x2 upsampling, align_corners=True (croco/models/dpt_block.py:215-216,320: F.interpolate(scale_factor=2,
+// mode="bilinear", align_corners=True)), NHWC fp32 in.  Same arithmetic as torch's upsample_bilinear2d: src = dst*(in-1)/(out-1),
+// out = (1-ly)[(1-lx) v00 + lx v01] + ly[(1-lx) v10 + lx v11].  Fused with what follows it in the head: an optional addend
+// (the skip connection "x0 + RCU1(x1)" of FeatureFusionBlock is out = up(x) + addend), an optional crop (dpt_head.py:57) and
+// the bf16 (hi, lo) split the next implicit-GEMM conv consumes.  One thread per (output pixel, 4 channels).
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(int B, int Hin, int Win, int C, int Hout, int Wout, const float* __restrict__ x,
+                  const float* __restrict__ addend, float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo) {
+    const int C4 = C >> 2;
+    const long long total = (long long)B * Hout * Wout * C4;
+    const float sh = (float)(Hin - 1) / (float)(2 * Hin - 1), sw = (float)(Win - 1) / (float)(2 * Win - 1);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(t % C4);
+        long long r = t / C4;
+        const int ox = (int)(r % Wout);
+        r /= Wout;
+        const int oy = (int)(r % Hout), b = (int)(r / Hout);
+        const float fy = sh * (float)oy, fx = sw * (float)ox;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.0f - ly, hx = 1.0f - lx;
+        const float4* base = reinterpret_cast<const float4*>(x) + (size_t)b * Hin * Win * C4 + c4;
+        const float4 v00 = base[((size_t)y0 * Win + x0) * C4], v01 = base[((size_t)y0 * Win + x1) * C4];
+        const float4 v10 = base[((size_t)y1 * Win + x0) * C4], v11 = base[((size_t)y1 * Win + x1) * C4];
+        float4 o;
+        o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+        o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+        o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+        o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+        const size_t oi = (size_t)t;            // float4 index into [B, Hout, Wout, C4]
+        if (addend) {
+            const float4 a = reinterpret_cast<const float4*>(addend)[oi];
+            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        if (y) reinterpret_cast<float4*>(y)[oi] = o;
+        if (hi) {
+            const float v[4] = {o.x, o.y, o.z, o.w};
+            __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                h4[k] = __float2bfloat16_rn(v[k]);
+                l4[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h4[k]));
+            }
+            reinterpret_cast<uint2*>(hi)[oi] = *reinterpret_cast<uint2*>(h4);
+            if (lo) reinterpret_cast<uint2*>(lo)[oi] = *reinterpret_cast<uint2*>(l4);
+        }
+    }
+}
+
+// Head epilogue (mast3r/catmlp_dpt_head.py:25-39,87-96 + dust3r/heads/postprocess.py:22-58) in one pass: reads the 4-channel
+// DPT map (NHWC) and the local-feature MLP output [B*S, 25*256] in its PRE-pixel-shuffle layout (channel c of pixel (Y,X) is
+// column c*256 + (Y%16)*16 + X%16 of token (Y/16)*(W/16) + X/16), and writes the post-processed dict directly:
+//   pts3d = xyz / max(|xyz|, 1e-8) * expm1(|xyz|)   conf = 1 + exp(c)   desc = d / |d|   desc_conf = exp(q).
+// Replaces pixel_shuffle + cat + 8 elementwise/reduction torch kernels and the [B,29,H,W] intermediate.
+template <int ND>
+__global__ void __launch_bounds__(256)
+head_postprocess_kernel(int B, int H, int W, const float* __restrict__ pts, const float* __restrict__ lf, long long ld_lf,
+                        float* __restrict__ pts3d, float* __restrict__ conf, float* __restrict__ desc,
+                        float* __restrict__ desc_conf) {
+    const long long total = (long long)B * H * W;
+    const int tw = W >> 4, S = (H >> 4) * tw;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(t % W);
+        const long long r = t / W;
+        const int Y = (int)(r % H), b = (int)(r / H);
+        const float4 p = reinterpret_cast<const float4*>(pts)[t];
+        const float d = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+        const float sc = expm1f(d) / fmaxf(d, 1e-8f);
+        pts3d[3 * t] = p.x * sc; pts3d[3 * t + 1] = p.y * sc; pts3d[3 * t + 2] = p.z * sc;
+        conf[t] = 1.0f + expf(p.w);
+        const float* row = lf + ((size_t)b * S + (size_t)(Y >> 4) * tw + (X >> 4)) * ld_lf + (Y & 15) * 16 + (X & 15);
+        float dv[ND];
+        float nrm = 0.f;
+#pragma unroll
+        for (int c = 0; c < ND; ++c) {
+            dv[c] = row[(size_t)c * 256];
+            nrm += dv[c] * dv[c];
+        }
+        const float inv = 1.0f / sqrtf(nrm);
+        float4* dp = reinterpret_cast<float4*>(desc + (size_t)t * ND);
+#pragma unroll
+        for (int c = 0; c < ND; c += 4) dp[c >> 2] = make_float4(dv[c] * inv, dv[c + 1] * inv, dv[c + 2] * inv, dv[c + 3] * inv);
+        desc_conf[t] = expf(row[(size_t)ND * 256]);
+    }
+}
+
 ADB_API int adb_layernorm(long long rows, int C, const float* x, const float* gamma, const float* beta, float eps,
                           float* y, void* y_hi, void* y_lo, cudaStream_t stream) {
     ADB_REQUIRE(rows >= 0 && C >= 8 && C <= 2048 && C % 8 == 0, "adb_layernorm: C must be a multiple of 8 in [8, 2048]");
@@ -386,5 +474,35 @@ ADB_API int adb_rope2d_inplace(int B, int N, int H, int D, long long stride_b, l
     rope2d_inplace_kernel<<<(unsigned)((long long)B * N), half * hy, 0, stream>>>(tokens, positions, N, H, D, stride_b,
                                                                                 stride_n, base, F0);
     ADB_CHECK_LAUNCH("rope2d_inplace_kernel");
+    return ADB_OK;
+}
+
+// x [B,Hin,Win,C] fp32 NHWC (C % 4 == 0) -> bilinear x2 (align_corners=True), cropped to [Hout<=2Hin, Wout<=2Win];
+// + addend [B,Hout,Wout,C] (may be NULL); y fp32 and/or (hi, lo) bf16 split outputs (each may be NULL).
+ADB_API int adb_upsample2x_nhwc(int B, int Hin, int Win, int C, int Hout, int Wout, const float* x, const float* addend,
+                                float* y, void* hi, void* lo, cudaStream_t stream) {
+    ADB_REQUIRE(B >= 0 && Hin >= 1 && Win >= 1 && C >= 4 && C % 4 == 0 && Hout >= 1 && Hout <= 2 * Hin && Wout >= 1 &&
+                    Wout <= 2 * Win, "adb_upsample2x_nhwc: bad sizes");
+    if (B == 0) return ADB_OK;
+    ADB_REQUIRE(x && (y || hi), "adb_upsample2x_nhwc: null pointer");
+    ADB_REQUIRE(!lo || hi, "adb_upsample2x_nhwc: lo without hi");
+    upsample2x_kernel<<<grid_for((long long)B * Hout * Wout * (C / 4)), 256, 0, stream>>>(
+        B, Hin, Win, C, Hout, Wout, x, addend, y, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    ADB_CHECK_LAUNCH("upsample2x_kernel");
+    return ADB_OK;
+}
+
+// pts [B,H,W,4] fp32, lf [B*(H/16)*(W/16), ld_lf >= (n_desc+1)*256] fp32 -> pts3d [B,H,W,3], conf [B,H,W],
+// desc [B,H,W,n_desc], desc_conf [B,H,W].  H, W multiples of 16; n_desc == 24 (the checkpoint ARTDECO loads).
+ADB_API int adb_head_postprocess(int B, int H, int W, const float* pts, const float* lf, long long ld_lf, int n_desc,
+                                 float* pts3d, float* conf, float* desc, float* desc_conf, cudaStream_t stream) {
+    ADB_REQUIRE(B >= 0 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0 && ld_lf >= (long long)(n_desc + 1) * 256,
+                "adb_head_postprocess: bad sizes");
+    ADB_REQUIRE(n_desc == 24, "adb_head_postprocess: only the desc24 head (output_mode pts3d+desc24) is built");
+    if (B == 0) return ADB_OK;
+    ADB_REQUIRE(pts && lf && pts3d && conf && desc && desc_conf, "adb_head_postprocess: null pointer");
+    head_postprocess_kernel<24><<<grid_for((long long)B * H * W), 256, 0, stream>>>(B, H, W, pts, lf, ld_lf, pts3d, conf,
+                                                                                   desc, desc_conf);
+    ADB_CHECK_LAUNCH("head_postprocess_kernel");
     return ADB_OK;
 }

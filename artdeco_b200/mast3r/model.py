@@ -110,6 +110,9 @@ class AsymmetricMASt3R:
                     # ConvTranspose2d [Cin, Cout, k, k] -> linear weight [(co, i, j), ci]
                     wt = v.to(dev).permute(1, 2, 3, 0).reshape(-1, v.shape[0]).contiguous()
                     self._w[k] = ops.split(wt, self.x3)
+                    bname = k[:-len(".weight")] + ".bias"     # one bias value per (cout, i, j) GEMM column
+                    if bname in raw:
+                        self._sd[bname + "_cols"] = raw[bname].float().repeat_interleave(v.shape[-1] * v.shape[-2]).contiguous().to(dev)
                 elif v.shape[-1] == 3:
                     self._w[k] = ops.prep_conv3x3_weight(v.to(dev), self.x3)
                 else:  # 1x1
@@ -278,30 +281,28 @@ class AsymmetricMASt3R:
     def _c1(self, x: Split, rows, name, **kw):
         return ops.linear(x, self._w[name + ".weight"], self._sd.get(name + ".bias"), rows, x3=self.x3, **kw)
 
-    @staticmethod
-    def _up2(x_nhwc):
-        y = F.interpolate(x_nhwc.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
-        return y.permute(0, 2, 3, 1).contiguous()
-
-    def _rcu(self, x_f32, x_relu: Split, B, H, W, pre, extra_residual=None, out_fp32=True, out_relu_split=False,
+    def _rcu(self, x_f32, x_relu: Split, B, H, W, pre, residual=None, out_fp32=True, out_relu_split=False,
              out_plain_split=False):
-        """ResidualConvUnit: conv2(relu(conv1(relu(x)))) + x (+ extra_residual)."""
+        """ResidualConvUnit: conv2(relu(conv1(relu(x)))) + residual (default: x itself)."""
         _, h = self._c3(x_relu, B, H, W, pre + ".conv1", act=2, want_fp32=False, want_split=True)
-        res = x_f32 if extra_residual is None else x_f32 + extra_residual
+        res = x_f32 if residual is None else residual
         return self._c3(h, B, H, W, pre + ".conv2", residual=res.contiguous(), want_fp32=out_fp32,
                         want_split=out_relu_split or out_plain_split, split_relu=out_relu_split)
 
-    def _fusion(self, pre, B, H, W, x0_f32, x0_relu: Split = None, x1=None):
+    def _fusion(self, pre, B, H, W, x0_f32=None, x0_relu: Split = None, x1=None, prev_lowres=None):
         """FeatureFusionBlock: [x0 + RCU1(x1)] -> RCU2 -> up x2 -> out_conv (the 1x1 commutes with the bilinear
-        upsampling, so it is applied at the low resolution: a quarter of the FLOPs, same result)."""
+        upsampling, so it is applied at the low resolution: a quarter of the FLOPs, same result).  Returns the LOW-resolution
+        out_conv output: the x2 upsampling is fused into the consumer (the next block's skip add, or the head's split), see
+        ops.upsample2x.  ``prev_lowres``: the previous block's low-resolution output, whose upsampling is this block's x0."""
         if x1 is not None:
             x1_f32, x1_relu = x1
-            x0_f32, x0_relu = self._rcu(x1_f32, x1_relu, B, H, W, pre + ".resConfUnit1", extra_residual=x0_f32,
-                                        out_relu_split=True)
+            # x0 + RCU1(x1) = conv2(.) + (x1 + up(prev)): the skip sum is produced by the upsampling kernel itself
+            res, _ = ops.upsample2x(prev_lowres, addend=x1_f32, out_hw=(H, W))
+            x0_f32, x0_relu = self._rcu(x1_f32, x1_relu, B, H, W, pre + ".resConfUnit1", residual=res, out_relu_split=True)
         _, o = self._rcu(x0_f32, x0_relu, B, H, W, pre + ".resConfUnit2", out_fp32=False, out_plain_split=True)
         y, _ = self._c1(Split(o.hi.view(B * H * W, -1), o.lo.view(B * H * W, -1) if o.lo is not None else None),
                         B * H * W, pre + ".out_conv")
-        return self._up2(y.view(B, H, W, -1))
+        return y.view(B, H, W, -1)
 
     def _dpt(self, pre, decout, H, W):
         l2 = self.cfg["dec_depth"]
@@ -314,9 +315,9 @@ class AsymmetricMASt3R:
         # act_postprocess: 1x1 convs are per-token linears; ConvTranspose(k=s) is a linear to (cout, i, j) + rearrangement
         def convT(t, name, k):
             cout = self._sd[name + ".bias"].shape[0]
-            r, _ = ops.linear(t, self._w[name + ".weight"], None, B * n, x3=self.x3)        # [B*n, cout*k*k]
-            r = r.view(B, nh, nw, cout, k, k).permute(0, 1, 4, 2, 5, 3).reshape(B, nh * k, nw * k, cout)
-            return (r + self._sd[name + ".bias"]).contiguous()
+            # bias folded into the GEMM epilogue (one value per (cout, i, j) column, expanded once in _prepare)
+            r, _ = ops.linear(t, self._w[name + ".weight"], self._sd[name + ".bias_cols"], B * n, x3=self.x3)   # [B*n, cout*k*k]
+            return r.view(B, nh, nw, cout, k, k).permute(0, 1, 4, 2, 5, 3).reshape(B, nh * k, nw * k, cout)
         _, t0 = self._c1(tok[0], B * n, ap + ".0.0", want_fp32=False, want_split=True)
         _, t1 = self._c1(tok[1], B * n, ap + ".1.0", want_fp32=False, want_split=True)
         l0 = convT(t0, ap + ".0.1", 4)                                                      # [B, 4nh, 4nw, 96]
@@ -336,13 +337,15 @@ class AsymmetricMASt3R:
                       B, nh, nw, rn + "3_rn", **kw)
         f3 = self._c3(ops.split(l3, self.x3), B, h3, w3, rn + "4_rn", **kw)
         sc = pre + ".scratch.refinenet"
-        p4 = self._fusion(sc + "4", B, h3, w3, f3[0], f3[1])[:, :nh, :nw].contiguous()
-        p3 = self._fusion(sc + "3", B, nh, nw, p4, x1=f2)
-        p2 = self._fusion(sc + "2", B, 2 * nh, 2 * nw, p3, x1=f1)
-        p1 = self._fusion(sc + "1", B, 4 * nh, 4 * nw, p2, x1=f0)                           # [B, 8nh, 8nw, 256]
-        o, _ = self._c3(ops.split(p1, self.x3), B, 8 * nh, 8 * nw, pre + ".head.0")
-        o = self._up2(o)                                                                    # [B, H, W, 128]
-        _, o = self._c3(ops.split(o, self.x3), B, H, W, pre + ".head.2", act=2, want_fp32=False, want_split=True)
+        # every block hands its LOW-resolution output on; the consumer's kernel upsamples (+ crop of dpt_head.py:57, + skip add)
+        q4 = self._fusion(sc + "4", B, h3, w3, f3[0], f3[1])
+        q3 = self._fusion(sc + "3", B, nh, nw, x1=f2, prev_lowres=q4)
+        q2 = self._fusion(sc + "2", B, 2 * nh, 2 * nw, x1=f1, prev_lowres=q3)
+        q1 = self._fusion(sc + "1", B, 4 * nh, 4 * nw, x1=f0, prev_lowres=q2)               # [B, 4nh, 4nw, 256] (low res)
+        _, p1 = ops.upsample2x(q1, want_fp32=False, want_split=True, x3=self.x3)           # [B, 8nh, 8nw, 256] split
+        o, _ = self._c3(p1, B, 8 * nh, 8 * nw, pre + ".head.0")
+        _, o = ops.upsample2x(o, want_fp32=False, want_split=True, x3=self.x3)             # [B, H, W, 128] split
+        _, o = self._c3(o, B, H, W, pre + ".head.2", act=2, want_fp32=False, want_split=True)
         out, _ = self._c1(Split(o.hi.view(B * H * W, -1), o.lo.view(B * H * W, -1) if o.lo is not None else None),
                           B * H * W, pre + ".head.4")
         return out.view(B, H, W, -1)                                                        # NHWC, 4 channels
@@ -366,6 +369,10 @@ class AsymmetricMASt3R:
             a = ops.split(cat.reshape(B * S, D), self.x3)
             _, hdn = self._linear(a, pre + ".head_local_features.fc1", B * S, act=1, want_fp32=False, want_split=True)
             lf, _ = self._linear(hdn, pre + ".head_local_features.fc2", B * S)
+            n_desc = lf.shape[-1] // 256 - 1
+            if not raw and n_desc == 24 and H % 16 == 0 and W % 16 == 0:
+                # pixel_shuffle + concat + postprocess in one kernel (csrc/vit_ops.cu head_postprocess_kernel)
+                return ops.head_postprocess(pts, lf, H, W, n_desc)
             lf = F.pixel_shuffle(lf.view(B, S, -1).transpose(-1, -2).reshape(B, -1, H // 16, W // 16), 16)
             fmap = torch.cat([pts, lf.permute(0, 2, 3, 1)], -1)             # B,H,W,29
             if raw:

@@ -20,6 +20,8 @@ _lib.register("adb_split_bf16", [i64, vp, vp, vp, vp])
 _lib.register("adb_rope_heads", [i32, i32, i32, i64, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp])
 _lib.register("adb_softmax_rows", [i64, i32, i64, i64, vp, vp, vp, vp])
 _lib.register("adb_im2col_patch16", [i32, i32, i32, vp, vp, vp, vp])
+_lib.register("adb_upsample2x_nhwc", [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp])
+_lib.register("adb_head_postprocess", [i32, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp])
 
 BF16 = torch.bfloat16
 
@@ -196,6 +198,41 @@ def conv3x3(x: Split, B: int, H: int, W: int, Cin: int, w: Split, bias, Cout: in
               _lib.ptr(sp.hi) if sp is not None else None,
               _lib.ptr(sp.lo) if (sp is not None and sp.lo is not None) else None, int(act), int(split_relu), _lib.stream())
     return out, sp
+
+
+def upsample2x(x: torch.Tensor, addend: torch.Tensor | None = None, out_hw=None, want_fp32=True, want_split=False, x3=True):
+    """Bilinear x2 (align_corners=True) of an NHWC fp32 tensor [B,H,W,C], + ``addend`` [B,Ho,Wo,C], cropped to ``out_hw``.
+    Returns (fp32 [B,Ho,Wo,C] or None, Split or None)."""
+    B, H, W, Cc = x.shape
+    Ho, Wo = (2 * H, 2 * W) if out_hw is None else out_hw
+    x = x.contiguous()
+    if addend is not None:
+        addend = addend.contiguous()
+        assert addend.shape == (B, Ho, Wo, Cc)
+    y = torch.empty(B, Ho, Wo, Cc, dtype=torch.float32, device=x.device) if want_fp32 else None
+    sp = None
+    if want_split:
+        sp = Split(torch.empty(B, Ho, Wo, Cc, dtype=BF16, device=x.device),
+                   torch.empty(B, Ho, Wo, Cc, dtype=BF16, device=x.device) if x3 else None)
+    _lib.call("adb_upsample2x_nhwc", B, H, W, Cc, Ho, Wo, _lib.ptr(x, torch.float32), _lib.ptr(addend), _lib.ptr(y),
+              _lib.ptr(sp.hi) if sp is not None else None, _lib.ptr(sp.lo) if (sp is not None and sp.lo is not None) else None,
+              _lib.stream())
+    return y, sp
+
+
+def head_postprocess(pts: torch.Tensor, lf: torch.Tensor, H: int, W: int, n_desc: int = 24):
+    """pts [B,H,W,4] fp32 (DPT map), lf [B*S, (n_desc+1)*256] fp32 (local-feature MLP output before pixel_shuffle) ->
+    dict(pts3d, conf, desc, desc_conf) as mast3r/catmlp_dpt_head.py:25-39 returns it."""
+    B = pts.shape[0]
+    dev = pts.device
+    pts, lf = pts.contiguous(), lf.contiguous()
+    res = dict(pts3d=torch.empty(B, H, W, 3, dtype=torch.float32, device=dev),
+               conf=torch.empty(B, H, W, dtype=torch.float32, device=dev),
+               desc=torch.empty(B, H, W, n_desc, dtype=torch.float32, device=dev),
+               desc_conf=torch.empty(B, H, W, dtype=torch.float32, device=dev))
+    _lib.call("adb_head_postprocess", B, H, W, _lib.ptr(pts, torch.float32), _lib.ptr(lf, torch.float32), lf.shape[-1], n_desc,
+              _lib.ptr(res["pts3d"]), _lib.ptr(res["conf"]), _lib.ptr(res["desc"]), _lib.ptr(res["desc_conf"]), _lib.stream())
+    return res
 
 
 def set_attention_variant(variant: int) -> int:

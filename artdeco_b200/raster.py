@@ -32,6 +32,9 @@ _lib.register("adb_raster_blend_bwd", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp
 _lib.register("adb_raster_project_bwd", [i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32,
                                          vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 
+_lib.register("adb_raster_project_bwd_multi", [i32, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+_lib.register("adb_raster_sh_bwd_multi", [i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp])
+
 _lib.register("adb_raster_project_fwd_legacy", [i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32,
                                                 vp, vp, vp, vp])
 _lib.register("adb_raster_isect_emit_legacy", [i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp])
@@ -41,6 +44,7 @@ _lib.register("adb_raster_blend_bwd_legacy", [i32, i32, i32, vp, vp, vp, vp, vp,
 
 TILE = 16
 SPLAT_STRIDE = 12
+COUNTER_COPIES = 4      # ADB_TILE_COUNTER_COPIES (csrc/raster_common.cuh)
 
 _ws_cache: dict = {}
 
@@ -61,14 +65,18 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H, eps2d, near, far, radius_clip,
-            legacy=False):
+            legacy=False, out=None):
     """Projection + SH + tile counts for one camera.  Returns radii[N,2] i32, splats[N,12], tiles_per_gauss[N].
-    ``legacy``: Inria conventions (see include/artdeco_b200.h, adb_raster_project_fwd_legacy)."""
+    ``legacy``: Inria conventions (see include/artdeco_b200.h, adb_raster_project_fwd_legacy).
+    ``out``: optional preallocated (radii, splats, tpg) — slices of per-camera stacks in the multi-view path."""
     N = means.shape[0]
     dev = means.device
-    radii = torch.empty(N, 2, dtype=torch.int32, device=dev)
-    splats = torch.empty(N, SPLAT_STRIDE, dtype=torch.float32, device=dev)
-    tpg = torch.empty(N, dtype=torch.int32, device=dev)
+    if out is not None:
+        radii, splats, tpg = out
+    else:
+        radii = torch.empty(N, 2, dtype=torch.int32, device=dev)
+        splats = torch.empty(N, SPLAT_STRIDE, dtype=torch.float32, device=dev)
+        tpg = torch.empty(N, dtype=torch.int32, device=dev)
     if legacy:
         _lib.call("adb_raster_project_fwd_legacy", N, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales),
                   _lib.ptr(opacities), _lib.ptr(sh), int(sh_degree), _lib.ptr(viewmat), _lib.ptr(K), _lib.ptr(campos),
@@ -109,7 +117,7 @@ def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=Fa
         return e64, e32, offsets, {"n_isect": torch.zeros(1, dtype=torch.int64, device=dev),
                                    "overflow": torch.zeros(1, dtype=torch.int32, device=dev)}
     if method == "bucket" and sort:
-        counts = torch.zeros(T, dtype=torch.int32, device=dev)
+        counts = torch.zeros(2 * COUNTER_COPIES * T, dtype=torch.int32, device=dev)   # counters | segment starts
         total = torch.zeros(1, dtype=torch.int64, device=dev)
         overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         cap_scan = int(capacity) if capacity is not None else 2147483646
@@ -178,8 +186,9 @@ def blend_forward(W, H, N, splats, vals, offsets, legacy=False):
     return colors, alphas, last_ids
 
 
-def blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas, legacy=False):
-    v_splats = torch.zeros(N, SPLAT_STRIDE, dtype=torch.float32, device=splats.device)
+def blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas, legacy=False, out=None):
+    """``out``: optional ZEROED [N,12] accumulator (a slice of the per-camera stack in the multi-view path)."""
+    v_splats = out if out is not None else torch.zeros(N, SPLAT_STRIDE, dtype=torch.float32, device=splats.device)
     _lib.call("adb_raster_blend_bwd_legacy" if legacy else "adb_raster_blend_bwd", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
               _lib.ptr(offsets), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(v_colors), _lib.ptr(v_alphas),
               _lib.ptr(v_splats), _lib.stream())
@@ -236,13 +245,130 @@ class _RasterizeOneCamera(torch.autograd.Function):
                 None, None, None, None, None, None, None, None, None)
 
 
+class _RasterizeCameras(torch.autograd.Function):
+    """C > 1 cameras of the same Gaussians (BASELINE config 4: an 8-view batch per optimiser step).  Forward: the
+    single-view stages per camera into stacked buffers.  Backward: blend_bwd per camera, then ONE multi-view projection
+    backward (parameters read once, 11 geometry gradients summed in registers) and ONE multi-view SH backward (v_sh
+    written once) instead of C single-view passes plus C-1 [N,59] accumulations (csrc/raster_project_bwd_multi.cu)."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, sh, viewmats, Ks, camposs, W, H, sh_degree, eps2d, near, far,
+                radius_clip, exchange=None):
+        _lib.require_cuda(means)
+        ctx.exchange = exchange
+        N, Cn = means.shape[0], viewmats.shape[0]
+        dev = means.device
+        with torch.cuda.device(dev):
+            radii = torch.empty(Cn, N, 2, dtype=torch.int32, device=dev)
+            splats = torch.empty(Cn, N, SPLAT_STRIDE, dtype=torch.float32, device=dev)
+            tpg = torch.empty(Cn, N, dtype=torch.int32, device=dev)
+            colors = torch.empty(Cn, H, W, 4, dtype=torch.float32, device=dev)
+            alphas = torch.empty(Cn, H, W, dtype=torch.float32, device=dev)
+            last_ids = torch.empty(Cn, H, W, dtype=torch.int32, device=dev)
+            keys_l, vals_l, offs_l = [], [], []
+            for c in range(Cn):
+                project(means, quats, scales, opacities, sh, sh_degree, viewmats[c], Ks[c], camposs[c], W, H, eps2d, near,
+                        far, radius_clip, out=(radii[c], splats[c], tpg[c]))
+                keys, vals, offsets, _ = intersect(radii[c], splats[c], tpg[c], W, H, c, Cn)
+                col, alp, last = blend_forward(W, H, N, splats[c], vals, offsets)
+                colors[c], alphas[c], last_ids[c] = col, alp, last
+                keys_l.append(keys)
+                vals_l.append(vals)
+                offs_l.append(offsets)
+        ctx.save_for_backward(means, quats, scales, opacities, sh, viewmats, Ks, camposs, radii, splats, alphas, last_ids,
+                              *vals_l, *offs_l)
+        ctx.cfg = (W, H, sh_degree, Cn)
+        isect_ids, flatten_ids = torch.cat(keys_l), torch.cat(vals_l)
+        base, offs_out = 0, []
+        for c in range(Cn):                        # gsplat offsets index the concatenated list
+            offs_out.append(offs_l[c][:-1] + base)
+            base += int(vals_l[c].numel())
+        isect_offsets = torch.stack(offs_out)
+        ctx.mark_non_differentiable(radii, splats, tpg, isect_ids, flatten_ids, isect_offsets)
+        return colors, alphas, radii, splats, tpg, isect_ids, flatten_ids, isect_offsets
+
+    @staticmethod
+    def backward(ctx, v_colors, v_alphas, *_unused):
+        W, H, sh_degree, Cn = ctx.cfg
+        saved = ctx.saved_tensors
+        means, quats, scales, opacities, sh, viewmats, Ks, camposs, radii, splats, alphas, last_ids = saved[:12]
+        vals_l, offs_l = saved[12:12 + Cn], saved[12 + Cn:12 + 2 * Cn]
+        N = means.shape[0]
+        dev = means.device
+        v_colors = torch.zeros(Cn, H, W, 4, device=dev) if v_colors is None else _f32c(v_colors)
+        v_alphas = torch.zeros(Cn, H, W, device=dev) if v_alphas is None else _f32c(v_alphas)
+        with torch.cuda.device(dev):
+            v_splats = torch.zeros(Cn, N, SPLAT_STRIDE, dtype=torch.float32, device=dev)
+            for c in range(Cn):
+                blend_backward(W, H, N, splats[c], vals_l[c], offs_l[c], alphas[c], last_ids[c], v_colors[c], v_alphas[c],
+                               out=v_splats[c])
+            ex = ctx.exchange
+            grads = multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, camposs, W, H, radii, splats,
+                                        v_splats, out=(dict(ex.views) if ex is not None else None), exchange=ex)
+        v_means, v_quats, v_scales, v_opac, v_sh, v_views, v_campos = grads
+        if ex is not None:      # the bucket is reused by the next step: hand autograd its own copies
+            v_means, v_quats, v_scales, v_opac = v_means.clone(), v_quats.clone(), v_scales.clone(), v_opac.clone()
+        return (v_means, v_quats, v_scales, v_opac, v_sh, v_views, None, v_campos, None, None, None, None, None, None, None,
+                None)
+
+
+def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, camposs, W, H, radii, splats, v_splats,
+                        out=None, exchange=None):
+    """Projection + SH backward for C stacked local views (csrc/raster_project_bwd_multi.cu).
+
+    ``out``: optional dict of preallocated gradient tensors (``v_means [N,3], v_quats [N,4], v_scales [N,3], v_opac [N],
+    v_sh [N,16,3]``), e.g. views of a flat communication bucket.
+    ``exchange`` (multi-GPU; ``parallel.MultiViewExchange``): the colour gradients of the local views are all-gathered while
+    the geometry kernel runs, the 11 geometry floats are all-reduced while the SH kernel expands the colour gradients of
+    EVERY rank's views; ``None`` = single process.  Returns (v_means, v_quats, v_scales, v_opac, v_sh, v_viewmats[C,4,4],
+    v_campos[C,3] of the local views)."""
+    N, Cn = means.shape[0], viewmats.shape[0]
+    dev = means.device
+    out = out or {}
+    v_means = out.get("v_means") if out.get("v_means") is not None else torch.empty_like(means)
+    v_quats = out.get("v_quats") if out.get("v_quats") is not None else torch.empty_like(quats)
+    v_scales = out.get("v_scales") if out.get("v_scales") is not None else torch.empty_like(scales)
+    v_opac = out.get("v_opac") if out.get("v_opac") is not None else torch.empty(N, dtype=torch.float32, device=dev)
+    v_sh = out.get("v_sh") if out.get("v_sh") is not None else torch.empty_like(sh)
+    v_views = torch.zeros(Cn, 4, 4, dtype=torch.float32, device=dev)
+    v_campos = torch.zeros(Cn, 3, dtype=torch.float32, device=dev)
+    Vc, Kc, Pc = _f32c(viewmats.detach()), _f32c(Ks.detach()), _f32c(camposs.detach())
+    # colour gradient masked by the SH clamp (rgb = max(.,0): zero gradient where the record's colour is 0); invisible
+    # Gaussians have zero accumulators.  Produced first so that its all-gather overlaps the geometry kernel.
+    g_rgb = out.get("g_rgb")
+    if g_rgb is None:
+        g_rgb = torch.empty(Cn, N, 3, dtype=torch.float32, device=dev)
+    torch.where(splats[..., 8:11] > 0, v_splats[..., 6:9], v_splats.new_zeros(()), out=g_rgb)
+    if exchange is not None:
+        exchange.start_gather(g_rgb, Pc)
+    _lib.call("adb_raster_project_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(Vc),
+              _lib.ptr(Kc), W, H, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(v_splats), _lib.ptr(v_means),
+              _lib.ptr(v_quats), _lib.ptr(v_scales), _lib.ptr(v_opac), None, _lib.ptr(v_views), _lib.stream())
+    if exchange is None:
+        _lib.call("adb_raster_sh_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(sh), int(sh_degree), _lib.ptr(Pc),
+                  _lib.ptr(g_rgb), _lib.ptr(v_sh), _lib.ptr(v_means), 1, _lib.ptr(v_campos), _lib.stream())
+        return v_means, v_quats, v_scales, v_opac, v_sh, v_views, v_campos
+    exchange.start_reduce()                       # geometry bucket (v_means | v_quats | v_scales | v_opac live in it)
+    g_all, P_all = exchange.wait_gather()
+    v_means_sh = exchange.scratch_means
+    _lib.call("adb_raster_sh_bwd_multi", N, int(g_all.shape[0]), _lib.ptr(means), _lib.ptr(sh), int(sh_degree),
+              _lib.ptr(P_all), _lib.ptr(g_all), _lib.ptr(v_sh), _lib.ptr(v_means_sh), 0, None, _lib.stream())
+    exchange.wait_reduce()
+    v_means.add_(v_means_sh)
+    return v_means, v_quats, v_scales, v_opac, v_sh, v_views, v_campos
+
+
 def rasterization(means: torch.Tensor, quats: torch.Tensor, scales: torch.Tensor, opacities: torch.Tensor,
                   colors: torch.Tensor, viewmats: torch.Tensor, Ks: torch.Tensor, width: int, height: int,
                   near_plane: float = 0.01, far_plane: float = 1e10, radius_clip: float = 0.0, eps2d: float = 0.3,
                   sh_degree: Optional[int] = None, packed: bool = False, tile_size: int = 16,
                   backgrounds: Optional[torch.Tensor] = None, render_mode: str = "RGB",
-                  rasterize_mode: str = "classic", absgrad: bool = False, **unsupported):
-    """See module docstring.  ``colors`` is SH [N,K,3] when ``sh_degree`` is given, else RGB [N,3]."""
+                  rasterize_mode: str = "classic", absgrad: bool = False, grad_exchange=None, **unsupported):
+    """See module docstring.  ``colors`` is SH [N,K,3] when ``sh_degree`` is given, else RGB [N,3].
+
+    ``grad_exchange`` (not in gsplat; multi-GPU view-parallel training, BASELINE config 4): a
+    ``parallel.MultiViewExchange``.  The backward then leaves on every rank the gradients summed over the views of ALL ranks
+    (all-gather of the colour gradients + all-reduce of the geometry gradients inside the multi-view backward)."""
     if unsupported:
         raise NotImplementedError(f"rasterization(): unsupported arguments {sorted(unsupported)}")
     if packed or absgrad or rasterize_mode != "classic" or tile_size != 16:
@@ -267,6 +393,25 @@ def rasterization(means: torch.Tensor, quats: torch.Tensor, scales: torch.Tensor
     else:
         assert colors.shape == (N, 3)
         direct = _f32c(colors)
+    th, tw = (height + TILE - 1) // TILE, (width + TILE - 1) // TILE
+    if grad_exchange is not None and sh is None:
+        raise NotImplementedError("grad_exchange needs SH colours (sh_degree given)")
+    if (C_ > 1 or grad_exchange is not None) and sh is not None:
+        # multi-view batch: stacked buffers, one multi-view projection/SH backward (see _RasterizeCameras)
+        Vs = _f32c(viewmats)
+        camposs = torch.inverse(Vs)[:, :3, 3].contiguous()
+        col, alp, radii, splats, tpg, isect_ids, flatten_ids, isect_offsets = _RasterizeCameras.apply(
+            means, quats, scales, opacities, sh, Vs, _f32c(Ks).detach(), camposs, int(width), int(height), int(sh_degree),
+            float(eps2d), float(near_plane), float(far_plane), float(radius_clip), grad_exchange)
+        if backgrounds is not None:
+            col = torch.cat([col[..., :3] + (1.0 - alp[..., None]) * backgrounds.view(C_, 1, 1, 3), col[..., 3:]], -1)
+        meta = {
+            "radii": radii, "means2d": splats[..., 0:2], "depths": splats[..., 11], "conics": splats[..., 2:5],
+            "opacities": opacities, "tiles_per_gauss": tpg, "isect_ids": isect_ids, "flatten_ids": flatten_ids,
+            "isect_offsets": isect_offsets.view(C_, th, tw),
+            "width": width, "height": height, "tile_size": TILE, "tile_width": tw, "tile_height": th, "n_cameras": C_,
+        }
+        return (col if render_mode == "RGB+D" else col[..., :3]), alp[..., None], meta
     out_c, out_a, radii_l, metas = [], [], [], []
     base = 0
     for c in range(C_):
@@ -284,7 +429,6 @@ def rasterization(means: torch.Tensor, quats: torch.Tensor, scales: torch.Tensor
         radii_l.append(radii)
         metas.append((splats, tpg, keys, vals, offs + base))  # gsplat offsets index the concatenated list
         base += int(vals.numel())
-    th, tw = (height + TILE - 1) // TILE, (width + TILE - 1) // TILE
     meta = {
         "radii": torch.stack(radii_l),
         "means2d": torch.stack([m[0][:, 0:2] for m in metas]),

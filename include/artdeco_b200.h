@@ -57,11 +57,27 @@ int adb_raster_sort(long long n_isect, int W, int H, int n_cams, int64_t* keys_a
                     int32_t* vals_b, void* ws, size_t ws_bytes, int* sorted_in_b /*HOST*/, adb_stream_t stream);
 int adb_raster_tile_offsets(long long n_isect, const int64_t* keys_sorted, int W, int H,
                             int32_t* tile_offsets /*[T+1]*/, adb_stream_t stream);
+/* Multi-view backward (BASELINE config 4: C views of the same Gaussians per optimiser step; csrc/raster_project_bwd_multi.cu).
+ * Same mathematics as C calls of adb_raster_project_bwd summed (gsplat's fully_fused_projection_bwd + spherical_harmonics_bwd
+ * under autograd's accumulation, h3dgsv3.py:664-680), with parameters read once and every gradient written once.
+ *   adb_raster_project_bwd_multi  radii [C,N,2], splats / v_splats [C,N,12], viewmats [C,16], Ks [C,9] (device).  v_means,
+ *       v_quats, v_scales, v_opac are OVERWRITTEN with the sum over cameras (geometry part only); g_rgb [C,N,3] = colour gradient
+ *       masked by the SH clamp and visibility (may be NULL); v_viewmats [C,16] ACCUMULATED.
+ *   adb_raster_sh_bwd_multi  v_sh [N,48] OVERWRITTEN with sum_c basis(dir_c) (x) g_rgb[c]; v_means += (or =) direction term;
+ *       v_campos [C,3] accumulated (may be NULL).  g_rgb / campos may include views rendered on other GPUs. */
+int adb_raster_project_bwd_multi(int N, int C, const float* means, const float* quats, const float* scales,
+                                 const float* viewmats, const float* Ks, int W, int H, const int32_t* radii,
+                                 const float* splats, const float* v_splats, float* v_means, float* v_quats, float* v_scales,
+                                 float* v_opac, float* g_rgb, float* v_viewmats, adb_stream_t stream);
+int adb_raster_sh_bwd_multi(int N, int C, const float* means, const float* sh, int sh_degree, const float* campos,
+                            const float* g_rgb, float* v_sh, float* v_means, int accumulate /* 0: v_means = term */,
+                            float* v_campos, adb_stream_t stream);
 /* Tile-bucketed intersection (no library sort, no host sync; bit-identical to adb_raster_isect_emit + adb_raster_sort +
  * adb_raster_tile_offsets, i.e. to gsplat's isect_tiles / radix sort / isect_offset_encode behind h3dgsv3.py:664-680):
  *   adb_raster_tile_count_scan   per-tile counts (RED.ADD) + one-CTA exclusive scan -> tile_offsets[T+1] clamped to
  *                                `capacity`; *total (int64, device) = true intersection count, *overflow (int32, device)
- *                                is SET when total > capacity.  tile_counts[T] must be zero on entry.
+ *                                is SET when total > capacity.  tile_counts: int32[2*4*T] (4 replicated counters per tile,
+ *                                then their segment starts); the first half must be zero on entry.
  *   adb_raster_tile_scatter_sort scatter depth_bits<<32|gaussian into each tile's segment (counters return to zero), then
  *                                one CTA per tile sorts its segment (bitonic, shared memory; global memory beyond 4096
  *                                entries) and writes keys = cam|tile|depth_bits, vals = cam*N + gaussian.
@@ -243,6 +259,16 @@ int adb_rope_heads(int B, int N, int h, long long ld, int col0, const float* x, 
 int adb_softmax_rows(long long rows, int L, long long ld_in, long long ld_out, const float* s, void* hi, void* lo,
                      adb_stream_t stream);
 int adb_im2col_patch16(int B, int H, int W, const float* img, void* hi, void* lo, adb_stream_t stream);
+/* DPT head companions.  adb_upsample2x_nhwc: F.interpolate(scale_factor=2, mode="bilinear", align_corners=True)
+ * (croco/models/dpt_block.py:215-216,320) on NHWC fp32, fused with the FeatureFusionBlock skip add (out = up(x) + addend),
+ * the crop of dpt_head.py:57 (Hout <= 2 Hin) and the bf16 split the next conv consumes; y / (hi, lo) may each be NULL.
+ * adb_head_postprocess: pixel_shuffle(16) + concat + postprocess of mast3r/catmlp_dpt_head.py:25-39,87-96 and
+ * dust3r/heads/postprocess.py:22-58 in one pass: pts [B,H,W,4] (DPT map) + lf [B*(H/16)*(W/16), ld_lf] (local-feature MLP
+ * output before the pixel shuffle, 25*256 columns) -> pts3d [B,H,W,3], conf [B,H,W], desc [B,H,W,24], desc_conf [B,H,W]. */
+int adb_upsample2x_nhwc(int B, int Hin, int Win, int C, int Hout, int Wout, const float* x, const float* addend, float* y,
+                        void* hi, void* lo, adb_stream_t stream);
+int adb_head_postprocess(int B, int H, int W, const float* pts, const float* lf, long long ld_lf, int n_desc, float* pts3d,
+                         float* conf, float* desc, float* desc_conf, adb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -58,6 +58,12 @@ def num_threads() -> int:
     return int(lib().adbo_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """Overrides OMP_NUM_THREADS for the C oracle (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().adbo_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def _f(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 

@@ -46,6 +46,15 @@ int adbo_num_threads(void) {
 #endif
 }
 
+/* bench.py --impl reference under torchrun inherits OMP_NUM_THREADS=1: the CPU arm sets its own thread count. */
+void adbo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static void quat_to_rot(const float* q, float* R /*9*/, float* inv_norm) {
     float w = q[0], x = q[1], y = q[2], z = q[3];
     float n2 = w * w + x * x + y * y + z * z;

@@ -45,7 +45,7 @@ def test_product_path_never_imports_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{py} imports the oracle"
     # the two sanctioned users outside tests/: smoke() and the bench's CPU legs -- and only inside those functions
     import ast
-    allowed = {"__graft_entry__.py": {"build", "smoke", "_smoke_mast3r"}, "bench.py": {"cpu_oracle_leg", "bench_mast3r"}}
+    allowed = {"__graft_entry__.py": {"build", "smoke", "_smoke_mast3r"}, "bench.py": {"cpu_oracle_leg", "cpu_mast3r_leg", "bench_mast3r", "bench_ops"}}
     for name, funcs in allowed.items():
         tree = ast.parse((ROOT / name).read_text())
         for node in tree.body:

@@ -37,6 +37,30 @@ def _worker(rank, world, port, q):
     gathered = [None] * world
     dist.all_gather_object(gathered, pairs)
     ok &= sorted(sum(gathered, [])) == list(range(7)) and max(map(len, gathered)) - min(map(len, gathered)) <= 1
+    # --- config-4 exchange: all-gather of per-view colour gradients + all-reduce of the 11 geometry floats ---
+    from artdeco_b200.parallel import GEOM_FLOATS, MultiViewExchange
+    Cl = 2
+    ex = MultiViewExchange(N, Cl, "cpu")
+    ok &= ex.geom.numel() == N * GEOM_FLOATS == N * 11 and ex.g_all.shape == (world * Cl, N, 3)
+    gr = torch.Generator().manual_seed(100 + rank)
+    g_loc, cam_loc = torch.randn(Cl, N, 3, generator=gr), torch.randn(Cl, 3, generator=gr)
+    geo_loc = {k: torch.randn(v.shape, generator=gr) for k, v in ex.views.items()}
+    for k, v in ex.views.items():
+        v.copy_(geo_loc[k])
+    ex.start_gather(g_loc, cam_loc)
+    ex.start_reduce()
+    g_all, cam_all = ex.wait_gather()
+    ex.wait_reduce()
+    exp_g, exp_c, exp_geo = [], [], {k: torch.zeros_like(v) for k, v in ex.views.items()}
+    for r in range(world):
+        g2 = torch.Generator().manual_seed(100 + r)
+        exp_g.append(torch.randn(Cl, N, 3, generator=g2))
+        exp_c.append(torch.randn(Cl, 3, generator=g2))
+        for k in exp_geo:
+            exp_geo[k] += torch.randn(exp_geo[k].shape, generator=g2)
+    ok &= torch.equal(g_all, torch.cat(exp_g)) and torch.equal(cam_all, torch.cat(exp_c))      # rank-major view order
+    for k in exp_geo:
+        ok &= bool(torch.allclose(ex.views[k], exp_geo[k], atol=1e-6))
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -144,6 +144,140 @@ def test_baseline_configs_fwd_bwd_match_oracle(cuda, N, view):
 
 
 @pytest.mark.gpu
+def test_multi_view_batch_equals_sum_of_single_views(cuda):
+    """BASELINE config 4 semantics (the step becomes "sum of C view losses"): rasterization() with C=3
+    viewmats must return per-view images identical to three C=1 calls, gsplat's concatenated isect ids with the camera bits
+    set, and parameter gradients equal to the SUM of the single-view gradients (multi-view projection/SH backward kernels),
+    plus per-camera viewmat gradients equal to the single-view ones."""
+    from artdeco_b200 import raster as R
+    N, W, H = 30000, 640, 352
+    sc = synthetic.raster_scene(N, seed=3)
+    cams = [synthetic.camera(W, H, view=v) for v in (0.0, 3.5, 7.0)]
+    Vs = torch.stack([c[0] for c in cams]).to(cuda)
+    Ks = torch.stack([c[1] for c in cams]).to(cuda)
+    g = torch.Generator().manual_seed(5)
+    vc, va = torch.randn(3, H, W, 4, generator=g).to(cuda), torch.randn(3, H, W, 1, generator=g).to(cuda)
+    tm = {k: sc[k].to(cuda).requires_grad_(True) for k in KEYS}
+    Vm = Vs.clone().requires_grad_(True)
+    cm, am, meta = R.rasterization(tm["means"], tm["quats"], tm["scales"], tm["opacities"], tm["sh"], Vm, Ks, W, H,
+                                   render_mode="RGB+D", sh_degree=3, eps2d=0.01)
+    assert cm.shape == (3, H, W, 4) and am.shape == (3, H, W, 1) and meta["radii"].shape == (3, N, 2)
+    ((cm * vc).sum() + (am * va).sum()).backward()
+    ts = {k: sc[k].to(cuda).requires_grad_(True) for k in KEYS}
+    tb = oracle.lib().adbo_tile_bits(W, H)
+    ids, flat = [], []
+    for c in range(3):
+        Vc = Vs[c].clone().requires_grad_(True)
+        c1, a1, m1 = R.rasterization(ts["means"], ts["quats"], ts["scales"], ts["opacities"], ts["sh"], Vc[None], Ks[c:c + 1], W,
+                                     H, render_mode="RGB+D", sh_degree=3, eps2d=0.01)
+        assert torch.equal(c1[0], cm[c]) and torch.equal(a1[0], am[c]) and torch.equal(m1["radii"][0], meta["radii"][c])
+        ((c1 * vc[c:c + 1]).sum() + (a1 * va[c:c + 1]).sum()).backward()
+        assert rel_err(Vm.grad[c], Vc.grad) < 1e-4, "per-camera viewmat gradient"
+        ids.append(m1["isect_ids"] | (c << (32 + tb)))
+        flat.append(m1["flatten_ids"] + c * N)
+    assert torch.equal(meta["isect_ids"], torch.cat(ids)) and torch.equal(meta["flatten_ids"], torch.cat(flat))
+    for k in KEYS:
+        # same per-pair arithmetic, different summation order over the three views: fp32 rounding only
+        assert rel_err(tm[k].grad, ts[k].grad) < 2e-5, k
+
+
+@pytest.mark.gpu
+def test_multi_view_exchange_algebra_matches_single_process(cuda):
+    """The multi-GPU exchange of parallel.MultiViewExchange (all-gather of 12 B colour gradients + all-reduce of the 11
+    geometry floats, SH gradient of every view expanded locally) emulated in one process: 4 views split over two "ranks"
+    must reproduce the single-process 4-view gradients."""
+    from artdeco_b200 import raster as R
+    N, W, H = 20000, 480, 272
+    sc = synthetic.raster_scene(N, seed=8)
+    cams = [synthetic.camera(W, H, view=v) for v in (1.0, 3.0, 5.0, 7.0)]
+    Vs = torch.stack([c[0] for c in cams]).to(cuda)
+    Ks = torch.stack([c[1] for c in cams]).to(cuda)
+    P = torch.inverse(Vs)[:, :3, 3].contiguous()
+    t = {k: sc[k].to(cuda) for k in KEYS}
+    g = torch.Generator().manual_seed(6)
+    vc, va = torch.randn(4, H, W, 4, generator=g).to(cuda), torch.randn(4, H, W, generator=g).to(cuda)
+
+    def local(cams_idx):
+        Cn = len(cams_idx)
+        radii = torch.empty(Cn, N, 2, dtype=torch.int32, device=cuda)
+        splats = torch.empty(Cn, N, 12, device=cuda)
+        tpg = torch.empty(Cn, N, dtype=torch.int32, device=cuda)
+        v_splats = torch.zeros(Cn, N, 12, device=cuda)
+        for j, c in enumerate(cams_idx):
+            R.project(t["means"], t["quats"], t["scales"], t["opacities"], t["sh"], 3, Vs[c], Ks[c], P[c], W, H, 0.01, 0.01,
+                      1e10, 0.0, out=(radii[j], splats[j], tpg[j]))
+            keys, vals, offs, _ = R.intersect(radii[j], splats[j], tpg[j], W, H)
+            col, alp, last = R.blend_forward(W, H, N, splats[j], vals, offs)
+            R.blend_backward(W, H, N, splats[j], vals, offs, alp, last, vc[c].contiguous(), va[c].contiguous(), out=v_splats[j])
+        return radii, splats, v_splats
+
+    idx_all = [0, 1, 2, 3]
+    ra, sa, va_ = local(idx_all)
+    full = R.multi_view_backward(t["means"], t["quats"], t["scales"], t["sh"], 3, Vs, Ks, P, W, H, ra, sa, va_)
+
+    class FakeExchange:            # what NCCL does, done by hand: "rank" 0 = views 0,1; "rank" 1 = views 2,3
+        def __init__(self):
+            self.scratch_means = torch.empty(N, 3, device=cuda)
+            self.g, self.p = [], []
+
+        def start_gather(self, g_rgb, campos):
+            self.g.append(g_rgb.clone()); self.p.append(campos.clone())
+
+        def start_reduce(self):
+            pass
+
+        def wait_gather(self):
+            return torch.cat(self.g_all), torch.cat(self.p_all)
+
+        def wait_reduce(self):
+            pass
+
+    # pass 1: each rank's local geometry gradients and colour gradients
+    parts = []
+    for ranks_views in ([0, 1], [2, 3]):
+        r_, s_, v_ = local(ranks_views)
+        ex = FakeExchange()
+        ex.g_all, ex.p_all = [torch.zeros(2, N, 3, device=cuda)] * 2, [P[ranks_views]] * 2     # placeholder gather
+        out = R.multi_view_backward(t["means"], t["quats"], t["scales"], t["sh"], 3, Vs[ranks_views], Ks[ranks_views],
+                                    P[ranks_views], W, H, r_, s_, v_, exchange=ex)
+        parts.append((ex.g[0], ex.p[0], [o.clone() for o in out[:4]], ex.scratch_means.clone()))
+    # zero colour gradients in the placeholder gather => out[0] = geometry-only v_means (+ 0): sum them like the all-reduce
+    geo = [sum(p[2][k] for p in parts) for k in range(4)]
+    g_all, p_all = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    v_sh = torch.empty(N, 16, 3, device=cuda)
+    v_means_sh = torch.empty(N, 3, device=cuda)
+    from artdeco_b200 import _lib
+    _lib.call("adb_raster_sh_bwd_multi", N, 4, _lib.ptr(t["means"]), _lib.ptr(t["sh"]), 3, _lib.ptr(p_all), _lib.ptr(g_all),
+              _lib.ptr(v_sh), _lib.ptr(v_means_sh), 0, None, _lib.stream())
+    assert rel_err(geo[0] + v_means_sh, full[0]) < 2e-5, "v_means"
+    assert rel_err(geo[1], full[1]) < 2e-5 and rel_err(geo[2], full[2]) < 2e-5 and rel_err(geo[3], full[3]) < 2e-5
+    assert rel_err(v_sh, full[4]) < 2e-5, "v_sh expanded from gathered colour gradients"
+
+
+@pytest.mark.gpu
+def test_intersect_capacity_mode_has_no_host_sync_and_flags_overflow(cuda):
+    """capacity mode of the tile-bucketed intersection: identical keys/vals/offsets without reading the count back, the true
+    count and an overflow flag stay on the device, and an undersized capacity is memory-safe and flagged."""
+    from artdeco_b200 import raster as R
+    N, W, H = 50000, 960, 540
+    sc, V, K = _scene(N, W, H, seed=1, view=2.0)
+    g = _gpu_stages(sc, V, K, W, H, cuda)
+    n = g["n"]
+    k2, v2, o2, info = R.intersect(g["radii"], g["splats"], g["tpg"], W, H, capacity=n + 1000)
+    assert int(info["n_isect"]) == n and int(info["overflow"]) == 0
+    assert torch.equal(k2[:n], g["keys"]) and torch.equal(v2[:n], g["vals"]) and torch.equal(o2, g["offs"])
+    kr, vr, orr, nr = R.intersect(g["radii"], g["splats"], g["tpg"], W, H, method="radix")
+    assert nr == n and torch.equal(kr, g["keys"]) and torch.equal(vr, g["vals"]) and torch.equal(orr, g["offs"]), \
+        "bucketed and radix paths must agree bit for bit"
+    k3, v3, o3, info3 = R.intersect(g["radii"], g["splats"], g["tpg"], W, H, capacity=n // 2)
+    assert int(info3["overflow"]) == 1 and int(info3["n_isect"]) == n and int(o3[-1]) == n // 2
+    m = int(o3[-1])
+    full_tiles = int((g["offs"] <= m).sum()) - 1          # tiles that fit entirely are still exact
+    assert torch.equal(k3[:int(g["offs"][full_tiles])], g["keys"][:int(g["offs"][full_tiles])])
+    torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
 def test_edge_cases(cuda):
     from artdeco_b200 import raster as R
     V, K = synthetic.camera(70, 50, focal=50.0)  # ragged: not a multiple of 16

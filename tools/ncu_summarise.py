@@ -60,6 +60,22 @@ def full(path):
         for w in WANT:
             if w in idx:
                 d[w] = f"{r[idx[w]]} {units[idx[w]]}".strip()
+        # warp-state statistics: cycles a warp spends stalled per issued instruction, by reason (top reasons only)
+        stalls = {}
+        for n, i in idx.items():
+            m = re.match(r"smsp__average_warps_issue_stalled_(\w+)_per_issue_active\.ratio", n)
+            if m:
+                try:
+                    stalls[m.group(1)] = round(float(r[i].replace(",", "")), 3)
+                except ValueError:
+                    pass
+        if stalls:
+            d["stall_cycles_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:8])
+        for n in ("smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__warps_eligible.avg.per_cycle_active",
+                  "smsp__issue_inst0.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum",
+                  "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum"):
+            if n in idx:
+                d[n] = f"{r[idx[n]]} {units[idx[n]]}".strip()
         res.append(d)
     print(json.dumps(res, indent=1))
 
