@@ -8,10 +8,33 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import i64, vp
+from ._lib import f32, i32, i64, vp
 
 _lib.register("adb_lod_select_workspace_bytes", [i64, C.POINTER(C.c_size_t)])
 _lib.register("adb_lod_select", [i64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp])
+
+
+_lib.register("adb_lod_weed_out", [i64, vp, vp, i32, vp, f32, vp, vp, vp])
+
+
+def weed_out_mask(xyz: torch.Tensor, d_max: torch.Tensor, cam_centres: torch.Tensor, visible_threshold: float,
+                  return_count: bool = False):
+    """``weed_out_gaussians`` (h3dgsv3.py:942-953) without the per-key-frame Python loop: ``cam_centres`` [K,3] are the
+    centres ``keyframe.get_Rt().T.inverse()[3,:3]`` of every key frame.  Returns the keep mask the reference hands to
+    ``optimizer.add_and_prune(make_dummy_ext_tensor(), weed_mask)`` (and the per-Gaussian visible count)."""
+    _lib.require_cuda(xyz)
+    N = xyz.shape[0]
+    dev = xyz.device
+    cams = cam_centres.detach().float().reshape(-1, 3).contiguous().to(dev)
+    if cams.shape[0] < 1:
+        raise ValueError("weed_out_mask needs at least one key frame")
+    keep = torch.empty(N, dtype=torch.bool, device=dev)
+    cnt = torch.empty(N, dtype=torch.int32, device=dev) if return_count else None
+    with torch.cuda.device(dev):
+        _lib.call("adb_lod_weed_out", N, _lib.ptr(xyz.detach().float().contiguous()),
+                  _lib.ptr(d_max.detach().float().reshape(-1).contiguous()), int(cams.shape[0]), _lib.ptr(cams),
+                  float(visible_threshold), _lib.ptr(cnt), _lib.ptr(keep), _lib.stream())
+    return (keep, cnt) if return_count else keep
 
 
 def lod_select(xyz: torch.Tensor, d_max: torch.Tensor, cam_centre: torch.Tensor):

@@ -58,11 +58,59 @@ class AsymmetricMASt3R:
             raise ValueError("head_dim must be 64")
 
     # ---- nn.Module-like surface the callers use -------------------------------------------------
+    # The reference hands the model object around: Frontend.py:29-30 (``load_mast3r(...)`` then ``.share_memory()`` before the
+    # tracker / backend processes are spawned), retrieval/model.py:123 (``for p in backbone.parameters(): p.requires_grad =
+    # False``), :200 (``backbone._encode_image``), mast3r/model.py:21-37 (``load_state_dict(ckpt['model'], strict=False)`` +
+    # ``.to(device)``).  This class is not an nn.Module (its weights live as bf16 splits behind a C ABI), so those entry
+    # points are provided explicitly with the same semantics.
     def eval(self):
         return self
 
-    def share_memory(self):
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("AsymmetricMASt3R (artdeco_b200) is inference-only, as every ARTDECO call site is")
         return self
+
+    def requires_grad_(self, requires_grad: bool = False):
+        for p in self.parameters():
+            p.requires_grad = requires_grad
+        return self
+
+    def share_memory(self):
+        """nn.Module.share_memory(): host tensors move to shared memory; CUDA tensors are left alone — exactly torch's
+        behaviour (``Tensor.share_memory_`` is a no-op for CUDA storage; they cross process boundaries as CUDA IPC handles
+        when the object is pickled by torch.multiprocessing, which ``__getstate__`` below supports)."""
+        for v in getattr(self, "_raw", {}).values():
+            if not v.is_cuda:
+                v.share_memory_()
+        return self
+
+    def named_parameters(self, prefix: str = "", recurse: bool = True):
+        for k, v in self._param_objs().items():
+            yield (prefix + ("." if prefix else "") + k, v)
+
+    def parameters(self, recurse: bool = True):
+        for _, v in self.named_parameters():
+            yield v
+
+    def state_dict(self, *args, **kwargs):
+        """fp32 tensors under the reference's key names (1017 keys for the ViT-L checkpoint)."""
+        from collections import OrderedDict
+        return OrderedDict((k, v) for k, v in getattr(self, "_raw", {}).items())
+
+    def _param_objs(self):
+        if getattr(self, "_params", None) is None:
+            self._params = {k: torch.nn.Parameter(v, requires_grad=False) for k, v in getattr(self, "_raw", {}).items()}
+        return self._params
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_streams"] = {}                 # CUDA streams are per process
+        st["_params"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
 
     def to(self, device):
         self.device = torch.device(device)
@@ -75,10 +123,21 @@ class AsymmetricMASt3R:
 
     @classmethod
     def from_pretrained(cls, path, **kw):
-        """Checkpoint layout of mast3r/model.py:21-37: a dict with 'model' (state dict) and 'args'."""
+        """Checkpoint layout of mast3r/model.py:21-37: a dict with 'model' (state dict) and 'args' (whose ``.model`` string
+        names the constructor call; only the sizes are read from it, the class is always this one)."""
         ckpt = torch.load(path, map_location="cpu", weights_only=False)
-        m = cls(**kw)
-        m.load_state_dict(ckpt["model"] if "model" in ckpt else ckpt, strict=False)
+        sd = ckpt["model"] if "model" in ckpt else ckpt
+        cfg = dict(kw)
+        args = ckpt.get("args") if isinstance(ckpt, dict) else None
+        spec = getattr(args, "model", args if isinstance(args, str) else None)
+        if isinstance(spec, str):
+            import re
+            for key in FULL_CFG:
+                m = re.search(rf"{key}\s*=\s*(\d+)", spec)
+                if m and key not in cfg:
+                    cfg[key] = int(m.group(1))
+        m = cls(**cfg)
+        m.load_state_dict(sd, strict=False)
         return m
 
     def load_state_dict(self, sd, strict: bool = False):
@@ -88,6 +147,7 @@ class AsymmetricMASt3R:
                 if k.startswith("dec_blocks."):
                     sd[k.replace("dec_blocks.", "dec_blocks2.", 1)] = v
         self._raw = {k: v.detach().float() for k, v in sd.items()}
+        self._params = None
         self._sd = None
         if self.device.type == "cuda":
             self._prepare()

@@ -413,6 +413,37 @@ def bench_ops(dev):
     return out
 
 
+def bench_config5(dev, world, rank):
+    """BASELINE config 5: raster_scene(10M) with the LoD d_max cull INSIDE the timed call, 4k evaluation
+    render (forward only, as the reference's evaluation renders are), one view per GPU (replicas by view, no collective)."""
+    import torch.distributed as dist
+    from artdeco_b200 import synthetic
+    from artdeco_b200.scene import render_lod
+    N5, W5, H5 = 10_000_000, 3840, 2160
+    sc = synthetic.raster_scene(N5, seed=0)
+    V, K = synthetic.camera(W5, H5, view=float(rank % 8))
+    kw = dict(xyz=sc["means"].to(dev), opacity=sc["opacities"][:, None].to(dev), f_dc=sc["sh"][:, :1].contiguous().to(dev),
+              f_rest=sc["sh"][:, 1:].contiguous().to(dev), scaling=sc["scales"].to(dev), rotation=sc["quats"].to(dev),
+              d_max=sc["d_max"].to(dev), tanfovx=W5 / (2 * float(K[0, 0])), tanfovy=H5 / (2 * float(K[1, 1])), sh_degree=3,
+              eps2d=0.01)
+    del sc
+    Vd = V.to(dev)
+    info = {}
+
+    def step():
+        with torch.no_grad():
+            pkg = render_lod(W5, H5, Vd, **kw)
+        info.update(n_selected=pkg["n_selected"], n_isect=pkg["n_isect"])
+    ms = timed(step, 5, 3, dev, world)
+    res = {"workload": "raster_scene(10M) + d_max ~ U(4,40), LoD cull inside the call, 3840x2160 forward render, one view per GPU",
+           "ms_per_render": ms, "value": world * W5 * H5 / (ms * 1e-3) / 1e9, "unit": "Gpix/s (forward only)",
+           "n_gaussians": N5, "n_selected": info["n_selected"], "n_isect": info["n_isect"],
+           "host_syncs_per_render": 2, "note": "public path: lod_select count + intersection count are read back (as gsplat does)"}
+    del kw
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -421,6 +452,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mast3r", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-3 stream and config-5 legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -597,6 +629,22 @@ def main():
     del params, t, engine, exchange, gt_buf
     torch.cuda.empty_cache()
     ops = bench_ops(dev) if (world == 1 and not args.no_cpu_baseline) else None
+    config5 = config3 = None
+    if not args.no_extra:
+        try:
+            log("config 5: 10M Gaussians, LoD cull, 4k render")
+            config5 = bench_config5(dev, world, rank)
+        except Exception as e:  # noqa: BLE001
+            config5 = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+        if world == 1 and not args.no_mast3r:
+            try:
+                log("config 3: synthetic stream (Frontend + mapper sharing the GPU)")
+                from artdeco_b200 import stream
+                config3 = stream.run(dev, frames=30, keyframe_every=5, grow=40000, mapper_iters=2)
+            except Exception as e:  # noqa: BLE001
+                config3 = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
 
     def make_line(mast3r, clocks):
         return {
@@ -620,6 +668,8 @@ def main():
             "roofline": roofline,
             "collective": collective,
             "ops": ops,
+            "config5_lod_4k": config5,
+            "config3_stream": config3,
             "mast3r": mast3r,
         }
 

@@ -191,6 +191,10 @@ int adb_adam_update(long long N, long long M, float* param, const float* grad, f
 int adb_lod_select_workspace_bytes(long long N, size_t* bytes /*HOST*/);
 int adb_lod_select(long long N, const float* xyz, const float* d_max, const float* cam /*[3]*/, unsigned char* mask,
                    float* ratio, int32_t* ids, int32_t* count, void* ws, size_t ws_bytes, adb_stream_t stream);
+/* weed_out_gaussians (Reconstruct/scene/scene_models/h3dgsv3.py:942-953) for ALL key frames in one pass: cams [K,3] camera
+ * centres (device); keep[i] = (#{k : |xyz_i - cam_k| < 2 d_max_i} / K > visible_threshold); visible_count [N] may be NULL. */
+int adb_lod_weed_out(long long N, const float* xyz, const float* d_max, int K, const float* cams, float visible_threshold,
+                     int32_t* visible_count, unsigned char* keep, adb_stream_t stream);
 
 /* ---- exact KNN on a grid hash ----
  * replaces SimpleKNN::knn (distCUDA2)        Reconstruct/submodules/simple-knn/simple_knn.cu:188-224, spatial.cu:16-26

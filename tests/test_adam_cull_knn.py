@@ -115,6 +115,28 @@ def test_lod_select_matches_reference_formula(cuda, N):
             assert_close(xg.grad, xr.grad, rtol=1e-5, what="v_xyz")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K", [(1, 1), (50_000, 7), (200_000, 40)])
+def test_weed_out_mask_matches_the_reference_loop(cuda, N, K):
+    """weed_out_gaussians (h3dgsv3.py:942-953) restated line for line with torch on the CPU (the per-key-frame loop IS the
+    reference code path) against the one-pass kernel; the same fp32 strict-'<' caveat as the LoD select applies."""
+    from artdeco_b200.cull import weed_out_mask
+    sc = synthetic.raster_scene(N, seed=5)
+    xyz, d_max = sc["means"], sc["d_max"] * 0.2
+    g = torch.Generator().manual_seed(3)
+    cams = torch.stack([torch.rand(K, generator=g) * 16 - 8, torch.rand(K, generator=g) * 9 - 4.5, torch.rand(K, generator=g) * 20], -1)
+    thr = 0.3
+    visible_count = torch.zeros(N, dtype=torch.int)
+    for k in range(K):
+        ob_dist = (xyz - cams[k]).norm(dim=1, keepdim=True)
+        visible_count += (ob_dist < 2 * d_max).squeeze(-1).int()
+    weed = (visible_count / K) > thr
+    keep, cnt = weed_out_mask(xyz.to(cuda), d_max.to(cuda), cams.to(cuda), thr, return_count=True)
+    dc = (cnt.cpu() != visible_count)
+    assert dc.sum() <= max(2, N * K // 100000), "visible counts (last-ulp distance ties only)"
+    assert ((keep.cpu() != weed) & ~dc).sum() == 0, "keep rule count/K > threshold"
+
+
 # ----------------------------------------------------------------------------- KNN (GPU) ----
 @pytest.mark.gpu
 @pytest.mark.parametrize("P,kind", [(5, "cloud"), (3000, "cloud"), (20000, "scene"), (4000, "plane"), (2000, "dups")])

@@ -148,3 +148,45 @@ def test_gemm_rope_epilogue_matches_separate_kernels(cuda, B, N, h, n_dst, tail)
     y = (x.double() @ w.double().T + bias.double()).view(B, N, -1)
     qd = y[..., :C].reshape(B, N, h, 64).transpose(1, 2)
     assert rel_err(q.hi.float() + q.lo.float(), mt.rope2d(qd, pos.cpu(), base=100.0)) < 3e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C,crop,add", [(2, 16, 16, 256, None, True), (1, 9, 13, 128, (17, 25), False), (1, 32, 32, 256, None, False),
+                                              (2, 8, 8, 256, (16, 16), True)])
+def test_upsample2x_matches_torch_interpolate(cuda, B, H, W, C, crop, add):
+    """adb_upsample2x_nhwc against F.interpolate(scale_factor=2, mode='bilinear', align_corners=True) exactly as the reference
+    calls it (croco/models/dpt_block.py:215-216,320), with the fused skip add, the crop of dpt_head.py:57 and the bf16 split."""
+    import torch.nn.functional as F
+    from artdeco_b200.mast3r import ops
+    x = _mk((B, H, W, C), 21, cuda)
+    Ho, Wo = crop if crop else (2 * H, 2 * W)
+    addend = _mk((B, Ho, Wo, C), 22, cuda) if add else None
+    ref = F.interpolate(x.double().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    ref = ref[:, :Ho, :Wo]
+    if add:
+        ref = ref + addend.double()
+    y, sp = ops.upsample2x(x, addend=addend, out_hw=crop, want_fp32=True, want_split=True)
+    assert y.shape == (B, Ho, Wo, C) and rel_err(y, ref) < 2e-6
+    assert rel_err(sp.hi.float() + sp.lo.float(), ref) < 2e-5
+
+
+@pytest.mark.gpu
+def test_head_postprocess_matches_reference_formulas(cuda):
+    """adb_head_postprocess against pixel_shuffle(16) + cat + postprocess written out as in mast3r/catmlp_dpt_head.py:25-39,
+    87-96 and dust3r/heads/postprocess.py:22-58 (fp64), including a large log-depth range for expm1."""
+    import torch.nn.functional as F
+    from artdeco_b200.mast3r import ops
+    B, H, W = 2, 48, 80
+    S = (H // 16) * (W // 16)
+    pts = _mk((B, H, W, 4), 31, cuda) * 2.0
+    lf = _mk((B * S, 25 * 256), 32, cuda)
+    res = ops.head_postprocess(pts, lf, H, W, 24)
+    l = F.pixel_shuffle(lf.double().view(B, S, -1).transpose(-1, -2).reshape(B, -1, H // 16, W // 16), 16)
+    fmap = torch.cat([pts.double(), l.permute(0, 2, 3, 1)], -1)
+    xyz = fmap[..., 0:3]
+    d = xyz.norm(dim=-1, keepdim=True)
+    assert rel_err(res["pts3d"], xyz / d.clip(min=1e-8) * torch.expm1(d)) < 1e-6
+    assert rel_err(res["conf"], 1 + fmap[..., 3].exp()) < 1e-6
+    desc = fmap[..., 4:28]
+    assert rel_err(res["desc"], desc / desc.norm(dim=-1, keepdim=True)) < 1e-6
+    assert rel_err(res["desc_conf"], fmap[..., 28].exp()) < 1e-6

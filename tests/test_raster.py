@@ -323,3 +323,46 @@ def test_full_size_properties_1m_1080p(cuda):
     sp2[:, 8:12] *= 2
     c2, a2, _ = R.blend_forward(1920, 1080, 1_000_000, sp2, vals, offs)
     assert torch.equal(a2, a) and torch.allclose(c2, 2 * g["colors"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
+def test_render_lod_matches_oracle_on_the_culled_subset(cuda):
+    """BASELINE config 5 at a reduced size: scene.render_lod (LoD d_max cull inside the call, h3dgsv3.py:617-700) must equal
+    the oracle's rasterisation of exactly the Gaussians the reference's cull formula keeps, with opacity x fade ratio; the
+    no-grad path (one fused gather) and the differentiable path (index_select) must agree bit for bit."""
+    from artdeco_b200.scene import render_lod
+    N, W, H = 120_000, 1280, 720
+    sc = synthetic.raster_scene(N, seed=2)
+    V, K = synthetic.camera(W, H, view=4.0)
+    d_max = sc["d_max"] * 0.25
+    cam = torch.inverse(V)[:3, 3]
+    dist = (sc["means"] - cam).norm(dim=1, keepdim=True)
+    sel = (dist < 2 * d_max).squeeze(-1)
+    amask = ((dist > d_max) & (dist < 2 * d_max)).squeeze(-1)
+    ratio = (2 * d_max - dist) / d_max
+    ratio[~amask] = 1.0
+    tanx, tany = W / (2 * float(K[0, 0])), H / (2 * float(K[1, 1]))
+    kw = dict(xyz=sc["means"].to(cuda), opacity=sc["opacities"][:, None].to(cuda), f_dc=sc["sh"][:, :1].to(cuda),
+              f_rest=sc["sh"][:, 1:].to(cuda), scaling=sc["scales"].to(cuda), rotation=sc["quats"].to(cuda), d_max=d_max.to(cuda),
+              tanfovx=tanx, tanfovy=tany, sh_degree=3, eps2d=0.01, bg=torch.tensor([0.1, 0.2, 0.3]))
+    with torch.no_grad():
+        pkg = render_lod(W, H, V.to(cuda), **kw)
+    mism = int((pkg["selection_mask"].cpu() != sel).sum())
+    assert mism <= 2, "cull mask (strict '<' on fp32 distances)"
+    if mism == 0:
+        f = oracle.rasterize_fwd(sc["means"][sel].numpy(), sc["quats"][sel].numpy(), sc["scales"][sel].numpy(),
+                                 (sc["opacities"][:, None] * ratio)[sel].squeeze(-1).numpy(), sc["sh"][sel].numpy(), V.numpy(),
+                                 K.numpy(), W, H)
+        ref = torch.from_numpy(f["colors"][..., :3]).permute(2, 0, 1) + (1 - torch.from_numpy(f["alphas"]))[None] * kw["bg"].view(3, 1, 1)
+        assert_close(pkg["render"], ref, what="render", max_outlier_frac=1e-4)
+        vis = torch.zeros(N, dtype=torch.bool)
+        vis[sel] = torch.from_numpy((f["radii"] > 0).any(1))
+        assert torch.equal(pkg["visibility_filter"].cpu(), vis)
+        assert pkg["n_isect"] == len(f["keys"])
+    kw2 = dict(kw)
+    kw2["opacity"] = kw["opacity"].clone().requires_grad_(True)
+    pkg2 = render_lod(W, H, V.to(cuda), **kw2)
+    assert torch.equal(pkg2["render"], pkg["render"]) and torch.equal(pkg2["invdepth"], pkg["invdepth"])
+    pkg2["render"].sum().backward()
+    assert kw2["opacity"].grad is not None and float(kw2["opacity"].grad.abs().sum()) > 0
+    assert float(kw2["opacity"].grad[~pkg["selection_mask"]].abs().sum()) == 0.0

@@ -128,3 +128,34 @@ def test_optimizer_oracle_on_a_hand_checked_case():
     assert torch.allclose(p.detach()[[0, 4]], exp) and torch.equal(p.detach()[1:4], before[1:4])
     assert torch.allclose(params["xyz"]["lr"][[0, 4], 0], torch.tensor([0.05, 0.05]))               # max(lr*0.1, 0.05)
     assert params["xyz"]["lr"][1:4].eq(torch.tensor([[0.25], [0.25], [0.5]])).all()
+
+
+def test_mast3r_mirror_has_the_module_surface_the_reference_touches(tmp_path):
+    """Boundary: mast3r/model.py:21-37 checkpoint round trip through from_pretrained, retrieval/model.py:123
+    freezing loop over backbone.parameters(), Frontend.py:29-30 share_memory() + hand-over to spawned processes (pickle)."""
+    import pickle
+    from types import SimpleNamespace
+    from artdeco_b200 import synthetic
+    from artdeco_b200.mast3r import AsymmetricMASt3R
+    from oracle import mast3r_torch as mt
+    cfg = mt.SMALL_CFG
+    sd = synthetic.det_weights(mt.param_shapes(cfg))
+    spec = ("AsymmetricMASt3R(pos_embed='RoPE100', patch_embed_cls='ManyAR_PatchEmbed', img_size=(512, 512), head_type='catmlp+dpt', "
+            + ", ".join(f"{k}={v}" for k, v in cfg.items()) + ", two_confs=True)")
+    ck = tmp_path / "ckpt.pth"
+    torch.save({"model": sd, "args": SimpleNamespace(model=spec)}, ck)
+    m = AsymmetricMASt3R.from_pretrained(str(ck))
+    assert all(getattr(m, k) == v for k, v in cfg.items()), "sizes come from the checkpoint's args string"
+    out = m.state_dict()
+    assert set(sd) <= set(out) and all(torch.equal(out[k], sd[k]) for k in sd)
+    assert any(k.startswith("dec_blocks2.") for k in out)            # cloned when absent (dust3r/model.py:90-97)
+    ps = list(m.parameters())
+    assert len(ps) == len(out) and all(isinstance(p, torch.nn.Parameter) for p in ps)
+    for p in m.parameters():                                         # retrieval/model.py:121-124
+        p.requires_grad = False
+    assert m.share_memory() is m and m.eval() is m and m.enc_embed_dim == cfg["enc_embed_dim"]
+    assert m.patch_embed.patch_size == (16, 16)
+    with pytest.raises(NotImplementedError):
+        m.train(True)
+    m2 = pickle.loads(pickle.dumps(m))                               # what mp.Process(args=(model,)) does
+    assert set(m2.state_dict()) == set(out) and m2._streams == {}
