@@ -51,6 +51,60 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// ---- TMA (bulk async copy) staging: "stage Gaussian attributes into shared memory via TMA" (BASELINE north_star) ----------
+// Each thread issues ONE 48-byte cp.async.bulk (global -> shared, SASS UBLKCP) for the record of its list entry of the NEXT
+// batch; completion is tracked by an mbarrier per buffer (every thread arrives once; issuing threads add expect_tx 48).
+// The copy engine fills buffer (b+1)&1 while the warps evaluate batch b from buffer b&1, so the dependent-load latency of the
+// gather (vals[idx] -> splats[g]) no longer sits between two block barriers.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Issues this thread's copy of record `g` into `rec` (48 B) or a plain arrival when the thread has no list entry.
+__device__ __forceinline__ void issue_record_copy(float4* rec, const float* __restrict__ splats, int g, bool have, uint64_t* bar) {
+    if (have) {
+        mbar_arrive_expect_tx(bar, ADB_SPLAT_STRIDE * 4);
+        bulk_copy_g2s(rec, splats + (size_t)g * ADB_SPLAT_STRIDE, ADB_SPLAT_STRIDE * 4, bar);
+    } else {
+        mbar_arrive(bar);
+    }
+}
+
+// In-place version of stage_record's pre-scaling for a record that arrived by bulk copy.
+template <bool LEGACY>
+__device__ __forceinline__ void prescale_record(float4* __restrict__ rec) {
+    float4 A = rec[0], B = rec[1];
+    A.z *= 0.5f * LOG2E;
+    A.w *= LOG2E;
+    B.x *= 0.5f * LOG2E;
+    B.z = (B.z - ADB_SIGMA_MARGIN) * LOG2E;
+    rec[0] = A;
+    rec[1] = B;
+    if (LEGACY) rec[2].w = 1.0f / rec[2].w;
+}
+
 // warp block geometry: warp w covers pixels x in [bx*16 + (w&1)*8, +8), y in [by*16 + (w>>1)*4, +4)
 struct WarpRect {
     float xlo, xhi, ylo, yhi;  // pixel-centre range
@@ -137,15 +191,17 @@ __device__ __forceinline__ int build_hit_list(const float4* __restrict__ sRec, u
 
 // LEGACY = Inria conventions (ADB_CONV_INRIA): alpha <= 0.99, stop when T(1-alpha) < 1e-4 (strict), 4th channel
 // accumulates 1/z, and main_ids gets the Gaussian with the largest blending weight alpha*T per pixel (-1: none).
-template <bool LEGACY>
+template <bool LEGACY, bool ASYNC>
 __global__ void __launch_bounds__(BLOCK, 4)
 blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* __restrict__ vals,
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
                  float* __restrict__ colors, float* __restrict__ alphas, int32_t* __restrict__ last_ids,
                  int32_t* __restrict__ main_ids) {
     constexpr float MAXA = LEGACY ? ADB_MAX_ALPHA_INRIA : ADB_MAX_ALPHA;
-    __shared__ __align__(16) float4 sRec[(BLOCK + 1) * 3];
+    constexpr int NBUF = ASYNC ? 2 : 1;
+    __shared__ __align__(16) float4 sRecBuf[NBUF][(BLOCK + 1) * 3];
     __shared__ __align__(8) unsigned short sList[NWARP][LIST_STRIDE];
+    __shared__ __align__(8) uint64_t sBar[2];
 
     const int tw = (W + ADB_TILE - 1) / ADB_TILE;
     const int tile = blockIdx.y * tw + blockIdx.x;
@@ -156,7 +212,23 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const WarpRect rect{(float)x0 + 0.5f, (float)x0 + 7.5f, (float)y0 + 0.5f, (float)y0 + 3.5f};
     const int start = tile_offsets[tile], end = tile_offsets[tile + 1];
-    if (tid == 0) write_dummy(sRec + DUMMY * 3);
+    if (tid == 0) {
+        write_dummy(sRecBuf[0] + DUMMY * 3);
+        if (ASYNC) {
+            write_dummy(sRecBuf[NBUF - 1] + DUMMY * 3);
+            mbar_init(&sBar[0], BLOCK);
+            mbar_init(&sBar[1], BLOCK);
+            fence_mbar_init();
+        }
+    }
+    const int nb = (end - start + BLOCK - 1) / BLOCK;
+    if (ASYNC) {
+        __syncthreads();
+        if (nb > 0) {       // prologue: batch 0 -> buffer 0
+            const int idx0 = start + tid;
+            issue_record_copy(sRecBuf[0] + tid * 3, splats, idx0 < end ? vals[idx0] % n_per_cam : 0, idx0 < end, &sBar[0]);
+        }
+    }
 
     float T = 1.0f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -164,12 +236,25 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     float best_w = 0.f;
     int best_k = -1;
     bool done = !inside;
-    const int nb = (end - start + BLOCK - 1) / BLOCK;
     for (int b = 0; b < nb; ++b) {
-        if (__syncthreads_count(done) >= BLOCK) break;   // also: every warp has finished reading the previous batch
+        const int n_done = __syncthreads_count(done);    // also: every warp has finished reading the previous batch
         const int bstart = start + b * BLOCK;
         const int idx = bstart + tid;
-        if (idx < end) stage_record<LEGACY>(sRec + tid * 3, splats, vals[idx] % n_per_cam);
+        float4* sRec = sRecBuf[ASYNC ? (b & 1) : 0];
+        if (ASYNC) {
+            if (n_done >= BLOCK) { mbar_wait(&sBar[b & 1], (b >> 1) & 1); break; }   // drain the copy in flight, then leave
+            if (b + 1 < nb) {                            // prefetch batch b+1 into the buffer batch b-1 has just released
+                const int idx1 = idx + BLOCK;
+                fence_proxy_async();
+                issue_record_copy(sRecBuf[(b + 1) & 1] + tid * 3, splats, idx1 < end ? vals[idx1] % n_per_cam : 0, idx1 < end,
+                                  &sBar[(b + 1) & 1]);
+            }
+            mbar_wait(&sBar[b & 1], (b >> 1) & 1);
+            if (idx < end) prescale_record<LEGACY>(sRec + tid * 3);
+        } else {
+            if (n_done >= BLOCK) break;
+            if (idx < end) stage_record<LEGACY>(sRec + tid * 3, splats, vals[idx] % n_per_cam);
+        }
         __syncthreads();
         const int bsize = min(BLOCK, end - bstart);
         if (__all_sync(FULL, done)) continue;
@@ -222,19 +307,23 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 }
 
 // Backward shared-memory layout (dynamic): S = slots per warp in the deferred-reduction buffer (16 or 32).
-template <int S>
+template <int S, bool ASYNC>
 struct BwdSmem {
+    static constexpr int NBUF = ASYNC ? 2 : 1;
     static constexpr int ROW4 = 17;                       // float4 per slot row: 32 x (vs, fac) + 1 pad -> conflict-free
-    static constexpr int OFF_REC = 0;                     // float4 [(BLOCK+1)*3]
-    static constexpr int OFF_G = OFF_REC + (BLOCK + 1) * 3 * 16;             // int [BLOCK + 4]
-    static constexpr int OFF_LIST = OFF_G + (BLOCK + 4) * 4;                  // u16 [NWARP][LIST_STRIDE]
+    static constexpr int REC_BYTES = (BLOCK + 1) * 3 * 16;
+    static constexpr int G_BYTES = (BLOCK + 4) * 4;
+    static constexpr int OFF_REC = 0;                     // float4 [NBUF][(BLOCK+1)*3]
+    static constexpr int OFF_G = OFF_REC + NBUF * REC_BYTES;                  // int [NBUF][BLOCK + 4]
+    static constexpr int OFF_BAR = OFF_G + NBUF * G_BYTES;                    // uint64 [2]
+    static constexpr int OFF_LIST = OFF_BAR + 16;                             // u16 [NWARP][LIST_STRIDE]
     static constexpr int OFF_VO = OFF_LIST + NWARP * LIST_STRIDE * 2;         // float4 [NWARP][32]
     static constexpr int OFF_V = OFF_VO + NWARP * 32 * 16;                    // float4 [NWARP][S*ROW4]
     static constexpr int BYTES = OFF_V + NWARP * S * ROW4 * 16;
-    static_assert(OFF_G % 16 == 0 && OFF_LIST % 16 == 0 && OFF_VO % 16 == 0 && OFF_V % 16 == 0, "alignment");
+    static_assert(OFF_G % 16 == 0 && OFF_BAR % 16 == 0 && OFF_LIST % 16 == 0 && OFF_VO % 16 == 0 && OFF_V % 16 == 0, "alignment");
 };
 
-template <bool LEGACY, int S, int OCC>
+template <bool LEGACY, int S, int OCC, bool ASYNC>
 __global__ void __launch_bounds__(BLOCK, OCC)
 blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* __restrict__ vals,
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
@@ -242,13 +331,14 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
                  const float* __restrict__ v_colors, const float* __restrict__ v_alphas,
                  float* __restrict__ v_splats) {
     constexpr float MAXA = LEGACY ? ADB_MAX_ALPHA_INRIA : ADB_MAX_ALPHA;
-    using L = BwdSmem<S>;
+    using L = BwdSmem<S, ASYNC>;
     constexpr int HALVES = 32 / S;          // lanes per slot in the reduction phase
     constexpr int ROWS = 4 / HALVES;        // pixel rows (of 8) each reduction lane walks
     static_assert(S == 16 || S == 32, "S");
     extern __shared__ __align__(16) unsigned char smem[];
     float4* sRec = reinterpret_cast<float4*>(smem + L::OFF_REC);
     int* sG = reinterpret_cast<int*>(smem + L::OFF_G);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
 
     const int tw = (W + ADB_TILE - 1) / ADB_TILE;
     const int tile = blockIdx.y * tw + blockIdx.x;
@@ -273,7 +363,17 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     float bv = 0.f;
     const float Tva = T_final * va;
     sVo[lane] = vo;
-    if (tid == 0) { write_dummy(sRec + DUMMY * 3); sG[DUMMY] = 0; }
+    if (tid == 0) {
+        write_dummy(sRec + DUMMY * 3);
+        sG[DUMMY] = 0;
+        if (ASYNC) {
+            write_dummy(reinterpret_cast<float4*>(smem + L::OFF_REC + L::REC_BYTES) + DUMMY * 3);
+            reinterpret_cast<int*>(smem + L::OFF_G + L::G_BYTES)[DUMMY] = 0;
+            mbar_init(&sBar[0], BLOCK);
+            mbar_init(&sBar[1], BLOCK);
+            fence_mbar_init();
+        }
+    }
 
     int warp_bin_final = bin_final;
 #pragma unroll
@@ -286,12 +386,35 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     float2* my_cell = reinterpret_cast<float2*>(sV) + lane;          // + slot * ROW4 * 2 (float2 units)
 
     const int nb = (end - start + BLOCK - 1) / BLOCK;
+    if (ASYNC) {
+        __syncthreads();
+        const int idx0 = end - 1 - tid;                      // prologue: batch 0 -> buffer 0
+        const int g0 = idx0 >= start ? vals[idx0] % n_per_cam : 0;
+        if (idx0 >= start) sG[tid] = g0;
+        issue_record_copy(sRec + tid * 3, splats, g0, idx0 >= start, &sBar[0]);
+    }
+    float4* const sRec0 = sRec;
+    int* const sG0 = sG;
     for (int b = 0; b < nb; ++b) {
         __syncthreads();  // previous batch fully consumed
         const int batch_end = end - 1 - b * BLOCK;           // smem slot t <-> sorted index batch_end - t (back to front)
         const int bsize = min(BLOCK, batch_end + 1 - start);
         const int idx = batch_end - tid;
-        if (idx >= start) {
+        if (ASYNC) {
+            sRec = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(sRec0) + (b & 1) * L::REC_BYTES);
+            sG = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(sG0) + (b & 1) * L::G_BYTES);
+            if (b + 1 < nb) {                                // prefetch batch b+1 into the buffer batch b-1 has just released
+                const int nbuf = (b + 1) & 1;
+                const int idx1 = idx - BLOCK;
+                const int g1 = idx1 >= start ? vals[idx1] % n_per_cam : 0;
+                if (idx1 >= start) reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(sG0) + nbuf * L::G_BYTES)[tid] = g1;
+                fence_proxy_async();
+                issue_record_copy(reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(sRec0) + nbuf * L::REC_BYTES) + tid * 3,
+                                  splats, g1, idx1 >= start, &sBar[nbuf]);
+            }
+            mbar_wait(&sBar[b & 1], (b >> 1) & 1);
+            if (idx >= start) prescale_record<LEGACY>(sRec + tid * 3);
+        } else if (idx >= start) {
             const int g = vals[idx] % n_per_cam;
             sG[tid] = g;
             stage_record<LEGACY>(sRec + tid * 3, splats, g);
@@ -400,12 +523,17 @@ static int blend_fwd_impl(bool legacy, int W, int H, int n_per_cam, const float*
     ADB_REQUIRE(W > 0 && H > 0 && n_per_cam >= 0, "adb_raster_blend_fwd: bad sizes");
     ADB_REQUIRE(tile_offsets && colors && alphas && last_ids, "adb_raster_blend_fwd: null pointer");
     dim3 grid(adb_cdiv(W, ADB_TILE), adb_cdiv(H, ADB_TILE));
+    // ADB_BLEND_TMA=0: synchronous LDG staging (A/B switch); default: double-buffered cp.async.bulk staging
+    static const int tma = getenv("ADB_BLEND_TMA") ? atoi(getenv("ADB_BLEND_TMA")) : 1;
     if (legacy)
-        blend_fwd_kernel<true><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
-                                                          colors, alphas, last_ids, main_ids);
+        blend_fwd_kernel<true, false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
+                                                                 colors, alphas, last_ids, main_ids);
+    else if (tma)
+        blend_fwd_kernel<false, true><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
+                                                                 colors, alphas, last_ids, nullptr);
     else
-        blend_fwd_kernel<false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
-                                                           colors, alphas, last_ids, nullptr);
+        blend_fwd_kernel<false, false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
+                                                                  colors, alphas, last_ids, nullptr);
     ADB_CHECK_LAUNCH("blend_fwd_kernel");
     return ADB_OK;
 }
@@ -426,18 +554,18 @@ ADB_API int adb_raster_blend_fwd_legacy(int W, int H, int n_per_cam, const float
                           stream);
 }
 
-template <bool LEGACY, int S, int OCC>
+template <bool LEGACY, int S, int OCC, bool ASYNC>
 static int launch_bwd(dim3 grid, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
                       const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids, const float* v_colors,
                       const float* v_alphas, float* v_splats, cudaStream_t stream) {
     static AdbDeviceOnce once;
     const int rc = once.ensure([]() -> int {
-        ADB_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<LEGACY, S, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      BwdSmem<S>::BYTES));
+        ADB_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<LEGACY, S, OCC, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      BwdSmem<S, ASYNC>::BYTES));
         return ADB_OK;
     });
     if (rc != ADB_OK) return rc;
-    blend_bwd_kernel<LEGACY, S, OCC><<<grid, BLOCK, BwdSmem<S>::BYTES, stream>>>(
+    blend_bwd_kernel<LEGACY, S, OCC, ASYNC><<<grid, BLOCK, BwdSmem<S, ASYNC>::BYTES, stream>>>(
         W, H, splats, vals_sorted, tile_offsets, n_per_cam, alphas, last_ids, v_colors, v_alphas, v_splats);
     return ADB_OK;
 }
@@ -456,10 +584,13 @@ static int blend_bwd_impl(bool legacy, int W, int H, int n_per_cam, const float*
     static const int occ = getenv("ADB_BWD_OCC") ? atoi(getenv("ADB_BWD_OCC")) : 4;
     int rc;
 #define ADB_BWD_ARGS grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors, v_alphas, v_splats, stream
-    if (legacy) rc = launch_bwd<true, 16, 3>(ADB_BWD_ARGS);
-    else if (slots == 32) rc = launch_bwd<false, 32, 2>(ADB_BWD_ARGS);
-    else if (occ == 4) rc = launch_bwd<false, 16, 4>(ADB_BWD_ARGS);
-    else rc = launch_bwd<false, 16, 3>(ADB_BWD_ARGS);
+    // ADB_BLEND_TMA: double-buffered cp.async.bulk staging (+13 KB of shared memory: 3 CTAs/SM instead of 4)
+    static const int tma = getenv("ADB_BLEND_TMA") ? atoi(getenv("ADB_BLEND_TMA")) : 1;
+    if (legacy) rc = launch_bwd<true, 16, 3, false>(ADB_BWD_ARGS);
+    else if (slots == 32) rc = launch_bwd<false, 32, 2, false>(ADB_BWD_ARGS);
+    else if (tma) rc = launch_bwd<false, 16, 3, true>(ADB_BWD_ARGS);
+    else if (occ == 4) rc = launch_bwd<false, 16, 4, false>(ADB_BWD_ARGS);
+    else rc = launch_bwd<false, 16, 3, false>(ADB_BWD_ARGS);
 #undef ADB_BWD_ARGS
     if (rc != ADB_OK) return rc;
     ADB_CHECK_LAUNCH("blend_bwd_kernel");

@@ -191,6 +191,20 @@ int adb_adam_update(long long N, long long M, float* param, const float* grad, f
 int adb_lod_select_workspace_bytes(long long N, size_t* bytes /*HOST*/);
 int adb_lod_select(long long N, const float* xyz, const float* d_max, const float* cam /*[3]*/, unsigned char* mask,
                    float* ratio, int32_t* ids, int32_t* count, void* ws, size_t ws_bytes, adb_stream_t stream);
+/* update_voxel (Reconstruct/scene/scene_models/h3dgsv3.py:227-316): voxel-hash class ids without the reference's three sorts
+ * (csrc/voxel.cu).  Tables are caller-allocated: vkeys[V], pkeys[P], ukeys[U] uint64 pre-filled with 0xFF bytes; pcount[P]
+ * int32 and best[V] uint64 zeroed; V, P powers of two >= 2N, U >= 2M.  mn = device float[3] minimum over all points.
+ *   adb_voxel_vote       original points -> cls_out[N] = majority class of each point's voxel (ties: smallest id)
+ *   adb_voxel_match_new  new points: voxel's class, or their voxel key collected into ulist (count in *ucount, device)
+ *   adb_voxel_rank_new   `sorted` = the distinct unmatched keys ascending (caller sorts) -> cls_out = base + rank */
+int adb_voxel_vote(long long N, const float* xyz, const long long* cls, const float* mn, float voxel_size, void* vkeys,
+                   long long V, void* pkeys, int* pcount, long long P, void* best, unsigned* slot_of, long long* cls_out,
+                   int* overflow, adb_stream_t stream);
+int adb_voxel_match_new(long long M, const float* new_xyz, const float* mn, float voxel_size, const void* vkeys, long long V,
+                        const void* best, int have_orig, void* ukeys, long long U, int* uslot_of, long long* cls_out,
+                        void* ulist, int* ucount, int* overflow, adb_stream_t stream);
+int adb_voxel_rank_new(long long M, int n, const void* sorted, const void* ukeys, long long U, int* urank,
+                       const int* uslot_of, long long base, long long* cls_out, adb_stream_t stream);
 /* weed_out_gaussians (Reconstruct/scene/scene_models/h3dgsv3.py:942-953) for ALL key frames in one pass: cams [K,3] camera
  * centres (device); keep[i] = (#{k : |xyz_i - cam_k| < 2 d_max_i} / K > visible_threshold); visible_count [N] may be NULL. */
 int adb_lod_weed_out(long long N, const float* xyz, const float* d_max, int K, const float* cams, float visible_threshold,
