@@ -104,11 +104,35 @@ class ClockSampler:
 
 
 def host_threads() -> int:
-    """Threads the CPU legs use: every host core, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
+    """Usable host cores for the CPU legs: min(affinity mask, cgroup CPU quota, physical cores).  Oversubscribing (e.g. one
+    thread per logical CPU of a box the container may only use a quarter of) makes OpenMP spin-wait and costs 5-15x."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = min(n, phys)
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
+def cpu_thread_setup():
+    """Leaves the default thread counts alone unless the launcher restricted them (torchrun exports OMP_NUM_THREADS=1)."""
+    want = host_threads()
+    if torch.get_num_threads() < max(2, want // 2):
+        torch.set_num_threads(want)
+    return want
 
 
 def cpu_oracle_leg(steps: int, warmup: int, n: int, views):
@@ -116,7 +140,10 @@ def cpu_oracle_leg(steps: int, warmup: int, n: int, views):
     Returns (Gpix/s, seconds/step, n_isect of the last view, threads)."""
     import oracle
     from artdeco_b200 import synthetic
-    threads = oracle.set_num_threads(host_threads())
+    want = cpu_thread_setup()
+    threads = oracle.num_threads()
+    if threads < max(2, want // 2):
+        threads = oracle.set_num_threads(want)
     sc = synthetic.raster_scene(n, seed=0)
     args = [sc[k].numpy() for k in KEYS]
     ts = []
@@ -143,7 +170,7 @@ def cpu_mast3r_leg(passes: int = 3):
     from artdeco_b200.mast3r import FULL_CFG
     from artdeco_b200.mast3r.shapes import random_state_dict
     from oracle import mast3r_torch as mt
-    torch.set_num_threads(host_threads())
+    cpu_thread_setup()
     sd_cpu = random_state_dict(FULL_CFG, "cpu", seed=0)
     g = torch.Generator().manual_seed(100)
     i1 = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1
