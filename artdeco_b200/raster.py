@@ -169,12 +169,16 @@ def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=Fa
     return keys[:n_isect], vals[:n_isect], offsets, n_isect
 
 
-def blend_forward(W, H, N, splats, vals, offsets, legacy=False):
-    """``legacy`` returns a 4th tensor main_ids[H,W] and accumulates 1/z in colors[...,3]."""
+def blend_forward(W, H, N, splats, vals, offsets, legacy=False, out=None):
+    """``legacy`` returns a 4th tensor main_ids[H,W] and accumulates 1/z in colors[...,3].
+    ``out``: optional preallocated (colors[H,W,4], alphas[H,W], last_ids[H,W]) — slices of per-camera stacks."""
     dev = splats.device
-    colors = torch.empty(H, W, 4, dtype=torch.float32, device=dev)
-    alphas = torch.empty(H, W, dtype=torch.float32, device=dev)
-    last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
+    if out is not None:
+        colors, alphas, last_ids = out
+    else:
+        colors = torch.empty(H, W, 4, dtype=torch.float32, device=dev)
+        alphas = torch.empty(H, W, dtype=torch.float32, device=dev)
+        last_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
     if legacy:
         main_ids = torch.empty(H, W, dtype=torch.int32, device=dev)
         _lib.call("adb_raster_blend_fwd_legacy", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
@@ -253,7 +257,7 @@ class _RasterizeCameras(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means, quats, scales, opacities, sh, viewmats, Ks, camposs, W, H, sh_degree, eps2d, near, far,
-                radius_clip, exchange=None):
+                radius_clip, exchange=None, capacities=None):
         _lib.require_cuda(means)
         ctx.exchange = exchange
         N, Cn = means.shape[0], viewmats.shape[0]
@@ -265,27 +269,32 @@ class _RasterizeCameras(torch.autograd.Function):
             colors = torch.empty(Cn, H, W, 4, dtype=torch.float32, device=dev)
             alphas = torch.empty(Cn, H, W, dtype=torch.float32, device=dev)
             last_ids = torch.empty(Cn, H, W, dtype=torch.int32, device=dev)
-            keys_l, vals_l, offs_l = [], [], []
+            keys_l, vals_l, offs_l, infos = [], [], [], []
             for c in range(Cn):
                 project(means, quats, scales, opacities, sh, sh_degree, viewmats[c], Ks[c], camposs[c], W, H, eps2d, near,
                         far, radius_clip, out=(radii[c], splats[c], tpg[c]))
-                keys, vals, offsets, _ = intersect(radii[c], splats[c], tpg[c], W, H, c, Cn)
-                col, alp, last = blend_forward(W, H, N, splats[c], vals, offsets)
-                colors[c], alphas[c], last_ids[c] = col, alp, last
+                cap = None if capacities is None else int(capacities[c] if hasattr(capacities, "__len__") else capacities)
+                keys, vals, offsets, info = intersect(radii[c], splats[c], tpg[c], W, H, c, Cn, capacity=cap)
+                blend_forward(W, H, N, splats[c], vals, offsets, out=(colors[c], alphas[c], last_ids[c]))
                 keys_l.append(keys)
                 vals_l.append(vals)
                 offs_l.append(offsets)
+                infos.append(info)
         ctx.save_for_backward(means, quats, scales, opacities, sh, viewmats, Ks, camposs, radii, splats, alphas, last_ids,
                               *vals_l, *offs_l)
         ctx.cfg = (W, H, sh_degree, Cn)
         isect_ids, flatten_ids = torch.cat(keys_l), torch.cat(vals_l)
         base, offs_out = 0, []
-        for c in range(Cn):                        # gsplat offsets index the concatenated list
+        for c in range(Cn):                        # gsplat offsets index the concatenated list (padded in capacity mode)
             offs_out.append(offs_l[c][:-1] + base)
             base += int(vals_l[c].numel())
         isect_offsets = torch.stack(offs_out)
-        ctx.mark_non_differentiable(radii, splats, tpg, isect_ids, flatten_ids, isect_offsets)
-        return colors, alphas, radii, splats, tpg, isect_ids, flatten_ids, isect_offsets
+        if capacities is None:
+            overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            overflow = torch.stack([i["overflow"] for i in infos]).amax(0)
+        ctx.mark_non_differentiable(radii, splats, tpg, isect_ids, flatten_ids, isect_offsets, overflow)
+        return colors, alphas, radii, splats, tpg, isect_ids, flatten_ids, isect_offsets, overflow
 
     @staticmethod
     def backward(ctx, v_colors, v_alphas, *_unused):
@@ -309,7 +318,7 @@ class _RasterizeCameras(torch.autograd.Function):
         if ex is not None:      # the bucket is reused by the next step: hand autograd its own copies
             v_means, v_quats, v_scales, v_opac = v_means.clone(), v_quats.clone(), v_scales.clone(), v_opac.clone()
         return (v_means, v_quats, v_scales, v_opac, v_sh, v_views, None, v_campos, None, None, None, None, None, None, None,
-                None)
+                None, None)
 
 
 def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, camposs, W, H, radii, splats, v_splats,
@@ -363,12 +372,18 @@ def rasterization(means: torch.Tensor, quats: torch.Tensor, scales: torch.Tensor
                   near_plane: float = 0.01, far_plane: float = 1e10, radius_clip: float = 0.0, eps2d: float = 0.3,
                   sh_degree: Optional[int] = None, packed: bool = False, tile_size: int = 16,
                   backgrounds: Optional[torch.Tensor] = None, render_mode: str = "RGB",
-                  rasterize_mode: str = "classic", absgrad: bool = False, grad_exchange=None, **unsupported):
+                  rasterize_mode: str = "classic", absgrad: bool = False, grad_exchange=None, isect_capacity=None,
+                  **unsupported):
     """See module docstring.  ``colors`` is SH [N,K,3] when ``sh_degree`` is given, else RGB [N,3].
 
     ``grad_exchange`` (not in gsplat; multi-GPU view-parallel training, BASELINE config 4): a
     ``parallel.MultiViewExchange``.  The backward then leaves on every rank the gradients summed over the views of ALL ranks
-    (all-gather of the colour gradients + all-reduce of the geometry gradients inside the multi-view backward)."""
+    (all-gather of the colour gradients + all-reduce of the geometry gradients inside the multi-view backward).
+
+    ``isect_capacity`` (not in gsplat; int or one int per camera): size the intersection buffers by this bound instead of reading
+    the count back — the call then has NO host sync (gsplat itself syncs on ``cum_tiles_per_gauss[-1].item()``).
+    ``meta["isect_ids"] / ["flatten_ids"]`` are then padded to the capacity per camera and ``meta["isect_overflow"]`` (int32[1] on
+    the device) is non-zero when a view needed more: read it together with the loss; the image of that view is then incomplete."""
     if unsupported:
         raise NotImplementedError(f"rasterization(): unsupported arguments {sorted(unsupported)}")
     if packed or absgrad or rasterize_mode != "classic" or tile_size != 16:
@@ -396,19 +411,21 @@ def rasterization(means: torch.Tensor, quats: torch.Tensor, scales: torch.Tensor
     th, tw = (height + TILE - 1) // TILE, (width + TILE - 1) // TILE
     if grad_exchange is not None and sh is None:
         raise NotImplementedError("grad_exchange needs SH colours (sh_degree given)")
-    if (C_ > 1 or grad_exchange is not None) and sh is not None:
+    if isect_capacity is not None and sh is None:
+        raise NotImplementedError("isect_capacity needs SH colours (sh_degree given)")
+    if (C_ > 1 or grad_exchange is not None or isect_capacity is not None) and sh is not None:
         # multi-view batch: stacked buffers, one multi-view projection/SH backward (see _RasterizeCameras)
         Vs = _f32c(viewmats)
         camposs = torch.inverse(Vs)[:, :3, 3].contiguous()
-        col, alp, radii, splats, tpg, isect_ids, flatten_ids, isect_offsets = _RasterizeCameras.apply(
+        col, alp, radii, splats, tpg, isect_ids, flatten_ids, isect_offsets, overflow = _RasterizeCameras.apply(
             means, quats, scales, opacities, sh, Vs, _f32c(Ks).detach(), camposs, int(width), int(height), int(sh_degree),
-            float(eps2d), float(near_plane), float(far_plane), float(radius_clip), grad_exchange)
+            float(eps2d), float(near_plane), float(far_plane), float(radius_clip), grad_exchange, isect_capacity)
         if backgrounds is not None:
             col = torch.cat([col[..., :3] + (1.0 - alp[..., None]) * backgrounds.view(C_, 1, 1, 3), col[..., 3:]], -1)
         meta = {
             "radii": radii, "means2d": splats[..., 0:2], "depths": splats[..., 11], "conics": splats[..., 2:5],
             "opacities": opacities, "tiles_per_gauss": tpg, "isect_ids": isect_ids, "flatten_ids": flatten_ids,
-            "isect_offsets": isect_offsets.view(C_, th, tw),
+            "isect_offsets": isect_offsets.view(C_, th, tw), "isect_overflow": overflow,
             "width": width, "height": height, "tile_size": TILE, "tile_width": tw, "tile_height": th, "n_cameras": C_,
         }
         return (col if render_mode == "RGB+D" else col[..., :3]), alp[..., None], meta

@@ -277,7 +277,7 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_baselines):
     from artdeco_b200 import _lib
     from artdeco_b200.mast3r import FULL_CFG, AsymmetricMASt3R, GraphedForwardPair, forward_pair
     from artdeco_b200.mast3r.shapes import random_state_dict
-    B = 4
+    B = int(os.environ.get("ADB_MAST3R_B", "4"))
     sd = random_state_dict(FULL_CFG, dev, seed=0)
     model = AsymmetricMASt3R(precision="bf16x3", **FULL_CFG).load_state_dict(sd).to(dev)
     g = torch.Generator().manual_seed(100 + rank)
@@ -525,6 +525,7 @@ def main():
 
     # per-stage live timing + launch count over K more steps, eager (CUDA events on the launching stream)
     engine.use_graph = False
+    ov, engine.overlap_views = engine.overlap_views, False     # one stream: per-kernel event times are not inflated by overlap
     _lib.TIMER = _lib.StageTimer()
     k_stage = max(2, min(args.steps, 5))
     for _ in range(k_stage):
@@ -534,6 +535,7 @@ def main():
     launches = _lib.TIMER.launches // k_stage * args.steps     # launches inside the timed region (graph replays the same nodes)
     _lib.TIMER = None
     engine.use_graph = True
+    engine.overlap_views = ov
     stage_ms = {k.replace("adb_raster_", ""): v[0] / v[1] for k, v in tot.items()}     # per LAUNCH
     stage_calls = {k.replace("adb_raster_", ""): v[1] // k_stage for k, v in tot.items()}
 
@@ -568,7 +570,7 @@ def main():
     params = {k: t[k].clone().requires_grad_(True) for k in KEYS}
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     h2d = gt_host.numel() * 4 + Cl * (16 + 9) * 4
-    d2h = 4
+    d2h = 8
     copy_stream = torch.cuda.Stream(device=dev)
     gt_buf = [torch.empty(Cl, H, W, 3, device=dev) for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
@@ -585,6 +587,8 @@ def main():
         used[slot].record()
     prefetch(0)
     exchange = engine.exchange
+    caps = list(engine.capacity)
+    flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
 
     def e2e_step():
         i = state["i"]
@@ -598,7 +602,7 @@ def main():
             p.grad = None
         colors, alphas, meta = R.rasterization(params["means"], params["quats"], params["scales"], params["opacities"],
                                                params["sh"], Ve, Ke, W, H, render_mode="RGB+D", sh_degree=3, eps2d=0.01,
-                                               grad_exchange=exchange)
+                                               grad_exchange=exchange, isect_capacity=caps)
         img = colors[..., :3]
         l1 = (img - gt).abs().mean()
         ssim = fused_ssim(img.permute(0, 3, 1, 2), gt.permute(0, 3, 1, 2))
@@ -606,9 +610,12 @@ def main():
         loss.backward()
         used[i % 2].record()
         loss_host.copy_(loss.detach(), non_blocking=True)
+        flag_host.copy_(meta["isect_overflow"], non_blocking=True)      # read back with the loss: no extra sync
 
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = timed(e2e_step, e2e_steps, 3, dev, world)
+    if int(flag_host):
+        raise SystemExit("e2e leg: intersection capacity exceeded")
     log(f"raster e2e leg done: {ms_e2e:.3f} ms/step")
 
     P = W * H
@@ -684,13 +691,14 @@ def main():
                              "236 MB) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"view-parallel dp{world}: 8-view batch split over ranks, one gradient exchange per step"
                                       + (" (all-gather 12 B/view colour grads + all-reduce [N,11], overlapped)" if world > 1 else ""),
-                       "graph": "local compute of the value leg replayed as one CUDA graph (no host sync inside the step)"},
+                       "graph": "local compute of the value leg replayed as one CUDA graph (no host sync inside the step); "
+                                "consecutive views on two streams inside the graph"},
             "clocks": clocks,
             "e2e": {"value": gpix_e2e, "unit": "Gpix/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "what": "rasterization(C local views)+L1+fused_ssim loss+backward via autograd (+ gradient exchange); per step: "
+                    "what": "rasterization(C local views, isect_capacity=...: no host sync)+L1+fused_ssim loss+backward via autograd (+ gradient exchange); per step: "
                             "the local views' gt images (prefetched on a copy stream, double-buffered) + cameras from pinned host "
-                            "memory, loss read back"},
+                            "memory, loss + overflow flag read back"},
             "gpu_launches": launches,
             "roofline": roofline,
             "collective": collective,
