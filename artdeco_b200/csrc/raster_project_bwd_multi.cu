@@ -256,71 +256,57 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
     Bx[15] = -0.5900435899266435f * fC2_x; By[15] = -0.5900435899266435f * fC2_y;
 }
 
-// Two lanes per Gaussian: lane h = tid & 1 owns SH coefficients k in [8h, 8h+8) (24 coefficient + 24 output registers instead
-// of 48 + 48: the one-thread-per-Gaussian version ran at 119 registers and 0.29 ms for 8 views of 1M Gaussians, far from its
-// 0.5 GB of traffic).  Both lanes evaluate the direction and the basis; the direction-gradient partial sums are combined with
-// one shuffle.  The pair reads / writes one contiguous 192 B row (96 B per lane).
-template <int HALF>
-__device__ __forceinline__ void sh_half_accumulate(const float* __restrict__ c24, float* __restrict__ o24, const float* Bs,
-                                                   const float* Bx, const float* By, const float* Bz, const float* g,
-                                                   float& vnx, float& vny, float& vnz) {
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-        const int k = HALF * 8 + kk;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float sv = c24[3 * kk + ch] * g[ch];
-            o24[3 * kk + ch] = fmaf(Bs[k], g[ch], o24[3 * kk + ch]);
-            vnx += Bx[k] * sv; vny += By[k] * sv; vnz += Bz[k] * sv;
-        }
-    }
-}
-
 __global__ void __launch_bounds__(PB)
 sh_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* __restrict__ sh, int sh_degree,
                     const float* __restrict__ campos, const float* __restrict__ g_rgb, float* __restrict__ v_sh,
                     float* __restrict__ v_means, int accumulate, float* __restrict__ v_campos) {
     __shared__ float sRed[PB / 32][3];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = t >> 1, half = t & 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < N;
     float mu[3] = {0.f, 0.f, 0.f};
-    float c24[24], o24[24];
+    float c48[48], o48[48];
 #pragma unroll
-    for (int k = 0; k < 24; ++k) { c24[k] = 0.f; o24[k] = 0.f; }
+    for (int k = 0; k < 48; ++k) { c48[k] = 0.f; o48[k] = 0.f; }
     if (in) {
         mu[0] = means[3 * i]; mu[1] = means[3 * i + 1]; mu[2] = means[3 * i + 2];
-        const float4* sp = reinterpret_cast<const float4*>(sh + (size_t)i * 48 + half * 24);
+        const float4* sp = reinterpret_cast<const float4*>(sh + (size_t)i * 48);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 12; ++k) {
             const float4 q = adb_ldg_stream4(sp + k);
-            c24[4 * k] = q.x; c24[4 * k + 1] = q.y; c24[4 * k + 2] = q.z; c24[4 * k + 3] = q.w;
+            c48[4 * k] = q.x; c48[4 * k + 1] = q.y; c48[4 * k + 2] = q.z; c48[4 * k + 3] = q.w;
         }
     }
     float gm[3] = {0.f, 0.f, 0.f};
+    // software pipeline: the colour gradient of view c+1 is in flight while view c is expanded.  (A two-lanes-per-Gaussian
+    // split of the 16 coefficients was measured SLOWER on B200: 0.42 vs 0.29 ms for 8 views — the duplicated basis evaluation
+    // costs more than the halved register footprint buys.)
+    float gn[3] = {0.f, 0.f, 0.f};
+    if (in) {
+        const float* gp = g_rgb + (size_t)i * 3;
+        gn[0] = gp[0]; gn[1] = gp[1]; gn[2] = gp[2];
+    }
     for (int c = 0; c < C; ++c) {
         float red[3] = {0.f, 0.f, 0.f};
-        float g[3] = {0.f, 0.f, 0.f};
-        if (in) {
-            const float* gp = g_rgb + ((size_t)c * N + i) * 3;
-            g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
+        const float g[3] = {gn[0], gn[1], gn[2]};
+        if (in && c + 1 < C) {
+            const float* gp = g_rgb + ((size_t)(c + 1) * N + i) * 3;
+            gn[0] = gp[0]; gn[1] = gp[1]; gn[2] = gp[2];
         }
-        const bool act = (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f);      // identical on both lanes of the pair
-        float vnx = 0.f, vny = 0.f, vnz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f, inv = 0.f;
-        if (act) {
+        if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {
             const float dx = mu[0] - campos[3 * c], dy = mu[1] - campos[3 * c + 1], dz = mu[2] - campos[3 * c + 2];
-            inv = rsqrtf(dx * dx + dy * dy + dz * dz);
-            nx = dx * inv; ny = dy * inv; nz = dz * inv;
+            const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+            const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
             float Bs[16], Bx[16], By[16], Bz[16];
             sh_basis_grad(sh_degree, nx, ny, nz, Bs, Bx, By, Bz);
-            if (half == 0) sh_half_accumulate<0>(c24, o24, Bs, Bx, By, Bz, g, vnx, vny, vnz);
-            else sh_half_accumulate<1>(c24, o24, Bs, Bx, By, Bz, g, vnx, vny, vnz);
-        }
-        // the two halves of the direction gradient meet here (the pair shares `act`, so the shuffle is convergent per pair)
-        vnx += __shfl_xor_sync(0xffffffffu, vnx, 1);
-        vny += __shfl_xor_sync(0xffffffffu, vny, 1);
-        vnz += __shfl_xor_sync(0xffffffffu, vnz, 1);
-        if (act && half == 0) {
+            float vnx = 0.f, vny = 0.f, vnz = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float sv = c48[3 * k + ch] * g[ch];
+                    o48[3 * k + ch] = fmaf(Bs[k], g[ch], o48[3 * k + ch]);
+                    vnx += Bx[k] * sv; vny += By[k] * sv; vnz += Bz[k] * sv;
+                }
             const float dot = vnx * nx + vny * ny + vnz * nz;
             const float gx = (vnx - dot * nx) * inv, gy = (vny - dot * ny) * inv, gz = (vnz - dot * nz) * inv;
             gm[0] += gx; gm[1] += gy; gm[2] += gz;
@@ -342,13 +328,11 @@ sh_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* 
         }
     }
     if (!in) return;
-    float4* op = reinterpret_cast<float4*>(v_sh + (size_t)i * 48 + half * 24);
+    float4* op = reinterpret_cast<float4*>(v_sh + (size_t)i * 48);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) op[k] = make_float4(o24[4 * k], o24[4 * k + 1], o24[4 * k + 2], o24[4 * k + 3]);
-    if (half == 0) {
-        if (accumulate) { v_means[3 * i] += gm[0]; v_means[3 * i + 1] += gm[1]; v_means[3 * i + 2] += gm[2]; }
-        else            { v_means[3 * i] = gm[0];  v_means[3 * i + 1] = gm[1];  v_means[3 * i + 2] = gm[2]; }
-    }
+    for (int k = 0; k < 12; ++k) op[k] = make_float4(o48[4 * k], o48[4 * k + 1], o48[4 * k + 2], o48[4 * k + 3]);
+    if (accumulate) { v_means[3 * i] += gm[0]; v_means[3 * i + 1] += gm[1]; v_means[3 * i + 2] += gm[2]; }
+    else            { v_means[3 * i] = gm[0];  v_means[3 * i + 1] = gm[1];  v_means[3 * i + 2] = gm[2]; }
 }
 
 }  // namespace
@@ -384,8 +368,8 @@ ADB_API int adb_raster_sh_bwd_multi(int N, int C, const float* means, const floa
     ADB_REQUIRE(N >= 0 && C >= 1 && sh_degree >= 0 && sh_degree <= 3, "adb_raster_sh_bwd_multi: bad sizes");
     if (N == 0) return ADB_OK;
     ADB_REQUIRE(means && sh && campos && g_rgb && v_sh && v_means, "adb_raster_sh_bwd_multi: null pointer");
-    sh_bwd_multi_kernel<<<adb_cdiv(2LL * N, PB), PB, 0, stream>>>(N, C, means, sh, sh_degree, campos, g_rgb, v_sh, v_means,
-                                                                 accumulate, v_campos);
+    sh_bwd_multi_kernel<<<adb_cdiv(N, PB), PB, 0, stream>>>(N, C, means, sh, sh_degree, campos, g_rgb, v_sh, v_means,
+                                                           accumulate, v_campos);
     ADB_CHECK_LAUNCH("sh_bwd_multi_kernel");
     return ADB_OK;
 }

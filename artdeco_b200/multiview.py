@@ -26,7 +26,7 @@ KEYS = ("means", "quats", "scales", "opacities", "sh")
 class MultiViewStep:
     def __init__(self, params: dict, viewmats: torch.Tensor, Ks: torch.Tensor, W: int, H: int, world: int = 1,
                  sh_degree: int = 3, eps2d: float = 0.01, near: float = 0.01, far: float = 1e10, radius_clip: float = 0.0,
-                 graph: bool = True, capacity_margin: float = 1.25, overlap_views: bool = True):
+                 graph: bool = True, capacity_margin: float = 1.25, overlap_views: bool = False):
         """``params``: dict of the five parameter tensors on the device; ``viewmats [C,4,4]``, ``Ks [C,3,3]``: the LOCAL
         views (``parallel.views_for_rank``).  ``world`` > 1 needs an initialised process group."""
         _lib.require_cuda(params["means"])
@@ -58,9 +58,10 @@ class MultiViewStep:
         self.capacity = None
         self.margin = capacity_margin
         self.use_graph = graph
-        # consecutive views run on two CUDA streams: the latency-bound stages of one view (projection, tile counting with L2
-        # atomics, scatter, per-tile sort: 10-15 % issue-slot utilisation) fill the gaps of the issue-bound blend kernels of the
-        # other.  Both streams fork from / join the caller's stream, so the pair is capturable in one CUDA graph.
+        # overlap_views=True runs consecutive views on two CUDA streams (the latency-bound projection / atomics / sort stages of
+        # one view could fill the gaps of the other's issue-bound blend kernels; both streams fork from / join the caller's, so
+        # the pair is capturable in one graph).  MEASURED on B200: 11.55 vs 10.99 ms per 8-view step — co-running blend kernels
+        # of two views cost more than the overlap wins — so it is off by default.
         self.overlap_views = overlap_views and self.C > 1
         self._side = torch.cuda.Stream(device=dev) if self.overlap_views else None
         self.graph = None

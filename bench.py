@@ -275,9 +275,9 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_baselines):
     """MASt3R pair inference (2x _encode_image + _decoder + 2x _downstream_head) at 512x512, B pairs per GPU per step;
     pairs are split across GPUs with no collective."""
     from artdeco_b200 import _lib
-    from artdeco_b200.mast3r import FULL_CFG, AsymmetricMASt3R, GraphedForwardPair, forward_pair
+    from artdeco_b200.mast3r import BENCH_PAIRS_PER_GPU, FULL_CFG, AsymmetricMASt3R, GraphedForwardPair, forward_pair
     from artdeco_b200.mast3r.shapes import random_state_dict
-    B = int(os.environ.get("ADB_MAST3R_B", "4"))
+    B = int(os.environ.get("ADB_MAST3R_B", str(BENCH_PAIRS_PER_GPU)))
     sd = random_state_dict(FULL_CFG, dev, seed=0)
     model = AsymmetricMASt3R(precision="bf16x3", **FULL_CFG).load_state_dict(sd).to(dev)
     g = torch.Generator().manual_seed(100 + rank)
@@ -350,7 +350,7 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_baselines):
                      "stage_ms": {k2.replace("adb_", ""): v[0] for k2, v in tot.items()}},
     }
     if want_baselines and rank == 0:
-        # the reference's own GPU mode on this box: torch eager fp32 with TF32 matmuls (croco.py:13 sets allow_tf32), B = 4
+        # the reference's own GPU mode on this box: torch eager fp32 with TF32 matmuls (croco.py:13 sets allow_tf32), same batch
         log("mast3r: reference GPU mode (torch eager fp32+TF32 restatement) on the same B200")
         try:
             from oracle import mast3r_torch as mt
@@ -362,8 +362,8 @@ def bench_mast3r(dev, world, rank, steps, warmup, want_baselines):
             torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
             res["gpu_reference"] = {"what": "oracle/mast3r_torch.forward_pair (the reference model restated op for op) in torch "
                                             "eager fp32+TF32 on the same GPU — the reference's own GPU mode (croco.py:13)",
-                                    "ms_per_step_b4": ms_ref, "pairs_per_s_b4": B / (ms_ref * 1e-3), "b1_latency_ms": ms_ref1,
-                                    "speedup_b4": ms_ref / ms, "speedup_b1": ms_ref1 / ms_b1}
+                                    "batch": B, "ms_per_step": ms_ref, "pairs_per_s": B / (ms_ref * 1e-3), "b1_latency_ms": ms_ref1,
+                                    "speedup_batched": ms_ref / ms, "speedup_b1": ms_ref1 / ms_b1}
         except Exception as e:  # noqa: BLE001
             res["gpu_reference"] = {"error": repr(e)[:200]}
     del graphed, model, sd
@@ -691,8 +691,7 @@ def main():
                              "236 MB) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"view-parallel dp{world}: 8-view batch split over ranks, one gradient exchange per step"
                                       + (" (all-gather 12 B/view colour grads + all-reduce [N,11], overlapped)" if world > 1 else ""),
-                       "graph": "local compute of the value leg replayed as one CUDA graph (no host sync inside the step); "
-                                "consecutive views on two streams inside the graph"},
+                       "graph": "local compute of the value leg replayed as one CUDA graph (no host sync inside the step)"},
             "clocks": clocks,
             "e2e": {"value": gpix_e2e, "unit": "Gpix/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,

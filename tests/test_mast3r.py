@@ -96,23 +96,23 @@ def test_cuda_model_matches_reference_golden_full(cuda):
 
 
 @pytest.mark.gpu
-def test_graphed_b4_replay_matches_golden_and_eager(cuda):
-    """The configuration bench.py times: GraphedForwardPair(model, 4, 512, 512) on two streams, REPLAYED (the race fixed
+def test_graphed_bench_batch_replay_matches_golden_and_eager(cuda):
+    """The configuration bench.py times: GraphedForwardPair(model, BENCH_PAIRS_PER_GPU, 512, 512) on two streams, REPLAYED (the race fixed
     in round 1 only showed under replay).  Batch item 0 is the golden pair, so all four outputs of both views are checked
     against the real reference's outputs (mast3r_full.pt); every output of the graph must be bit-identical to the eager
     forward_pair on the same batch, on the first and on the second replay (utils_mast3r.py:30-36 is the eager call)."""
-    from artdeco_b200.mast3r import AsymmetricMASt3R, GraphedForwardPair, forward_pair
+    from artdeco_b200.mast3r import BENCH_PAIRS_PER_GPU as B, AsymmetricMASt3R, GraphedForwardPair, forward_pair
     g = _gold("full")
     s, H, W = g["stride"], g["H"], g["W"]
     sd = synthetic.det_weights(mt.param_shapes(g["cfg"]))
     m = AsymmetricMASt3R(precision="bf16x3", **g["cfg"]).load_state_dict(sd).to(cuda)
     a1, a2 = synthetic.mast3r_pair(1, H, W, seed=0)
-    r1, r2 = synthetic.mast3r_pair(3, H, W, seed=21)
+    r1, r2 = synthetic.mast3r_pair(B - 1, H, W, seed=21)
     i1, i2 = torch.cat((a1, r1)).to(cuda), torch.cat((a2, r2)).to(cuda)
     e1, e2 = forward_pair(m, i1, i2)
     e1 = {k: v.clone() for k, v in e1.items()}
     e2 = {k: v.clone() for k, v in e2.items()}
-    graphed = GraphedForwardPair(m, 4, H, W)
+    graphed = GraphedForwardPair(m, B, H, W)
     for replay in range(2):
         if replay == 1:      # a different batch in between, so that replay 2 cannot pass on stale buffers
             graphed(i2, i1)
