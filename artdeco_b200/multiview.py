@@ -70,11 +70,24 @@ class MultiViewStep:
         self.v_views = self.v_campos = None
 
     # ---- stages -----------------------------------------------------------------------------------------------------
-    def _local_views(self, capacity):
-        """projection -> intersection -> blend fwd -> blend bwd for every local view; no host sync when capacity is given."""
+    def _view(self, c, capacity):
+        """projection -> intersection -> blend fwd -> blend bwd -> masked colour gradient of local view c."""
         sh_degree, eps2d, near, far, rclip = self.cfg
         p, W, H, N = self.p, self.W, self.H, self.N
-        self.v_splats.zero_()
+        self.v_splats[c].zero_()
+        R.project(p["means"], p["quats"], p["scales"], p["opacities"], p["sh"], sh_degree, self.V[c], self.K[c], self.P[c],
+                  W, H, eps2d, near, far, rclip, out=(self.radii[c], self.splats[c], self.tpg[c]))
+        cap = None if capacity is None else capacity[c]
+        keys, vals, offs, info = R.intersect(self.radii[c], self.splats[c], self.tpg[c], W, H, capacity=cap)
+        col, alp, last = R.blend_forward(W, H, N, self.splats[c], vals, offs)
+        R.blend_backward(W, H, N, self.splats[c], vals, offs, alp, last, self.v_colors[c], self.v_alphas[c],
+                         out=self.v_splats[c])
+        if self.exchange is not None:
+            R.mask_rgb_grad(self.splats[c], self.v_splats[c], self.grads["g_rgb"][c])
+        return col, alp, info, (keys, vals, offs, last)
+
+    def _local_views(self, capacity):
+        """Every local view; no host sync when capacity is given."""
         cols, alps, infos = [None] * self.C, [None] * self.C, [None] * self.C
         cur = torch.cuda.current_stream(self.dev)
         two = self.overlap_views and capacity is not None       # the calibration pass syncs per view: keep it on one stream
@@ -83,15 +96,9 @@ class MultiViewStep:
         for c in range(self.C):
             st = self._side if (two and (c & 1)) else cur
             with torch.cuda.stream(st):
-                R.project(p["means"], p["quats"], p["scales"], p["opacities"], p["sh"], sh_degree, self.V[c], self.K[c],
-                          self.P[c], W, H, eps2d, near, far, rclip, out=(self.radii[c], self.splats[c], self.tpg[c]))
-                cap = None if capacity is None else capacity[c]
-                keys, vals, offs, info = R.intersect(self.radii[c], self.splats[c], self.tpg[c], W, H, capacity=cap)
-                col, alp, last = R.blend_forward(W, H, N, self.splats[c], vals, offs)
-                R.blend_backward(W, H, N, self.splats[c], vals, offs, alp, last, self.v_colors[c], self.v_alphas[c],
-                                 out=self.v_splats[c])
+                col, alp, info, tmp = self._view(c, capacity)
                 if two and st is not cur:
-                    for tns in (keys, vals, offs, col, alp, last):
+                    for tns in tmp + (col, alp):
                         tns.record_stream(cur)
             cols[c], alps[c], infos[c] = col, alp, info
         if two:
@@ -124,12 +131,27 @@ class MultiViewStep:
                 self._backward()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            cols, alps, infos = self._local_views(self.capacity)
-            if self.exchange is None:
+        if self.exchange is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cols, alps, infos = self._local_views(self.capacity)
                 self._backward()
-        self.graph, self.render, self.info = g, (cols, alps), infos
+            self.graph, self.render, self.info = [g], (cols, alps), infos
+            return
+        # multi-GPU: one graph PER VIEW, so that view c's colour gradients can be all-gathered (NCCL, outside the graphs)
+        # while view c+1 renders
+        graphs, cols, alps, infos = [], [], [], []
+        pool = None
+        for c in range(self.C):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                col, alp, info, _ = self._view(c, self.capacity)
+            pool = g.pool()
+            graphs.append(g)
+            cols.append(col)
+            alps.append(alp)
+            infos.append(info)
+        self.graph, self.render, self.info = graphs, (cols, alps), infos
 
     # ---- public -----------------------------------------------------------------------------------------------------
     def set_upstream(self, v_colors: torch.Tensor, v_alphas: torch.Tensor):
@@ -146,11 +168,22 @@ class MultiViewStep:
             if self.use_graph:
                 if self.graph is None:
                     self._capture()
-                self.graph.replay()
-                if self.exchange is not None:
-                    self._backward()                    # 2 kernels + 2 collectives, eager (NCCL outside the graph)
+                if self.exchange is None:
+                    self.graph[0].replay()
+                else:
+                    for c, g in enumerate(self.graph):
+                        g.replay()
+                        self.exchange.start_gather_view(c, self.grads["g_rgb"][c], self.P if c == 0 else None)
+                    self._backward()                    # 2 kernels + the all-reduce, eager (NCCL outside the graphs)
             else:
-                cols, alps, infos = self._local_views(self.capacity)
+                cols, alps, infos = [], [], []
+                for c in range(self.C):
+                    col, alp, info, _ = self._view(c, self.capacity)
+                    if self.exchange is not None:
+                        self.exchange.start_gather_view(c, self.grads["g_rgb"][c], self.P if c == 0 else None)
+                    cols.append(col)
+                    alps.append(alp)
+                    infos.append(info)
                 self.render, self.info = (cols, alps), infos
                 self._backward()
         return self.grads

@@ -65,29 +65,54 @@ class MultiViewExchange:
             v = self.geom[o:o + n_gaussians * m]
             self.views[name] = v.view(n_gaussians, m) if m > 1 else v
             o += n_gaussians * m
-        self.g_all = torch.empty(self.world * views_local, n_gaussians, 3, dtype=torch.float32, device=device)
-        self.campos_all = torch.empty(self.world * views_local, 3, dtype=torch.float32, device=device)
+        # gathered colour gradients, VIEW-major: g_all[c, r] = view c of rank r (one contiguous all-gather output per local view,
+        # so that a view's gather can start as soon as ITS blend backward has finished, while the next view is still rendering)
+        self.g_all = torch.empty(views_local, self.world, n_gaussians, 3, dtype=torch.float32, device=device)
+        self.campos_all = torch.empty(views_local, self.world, 3, dtype=torch.float32, device=device)
         self.scratch_means = torch.empty(n_gaussians, 3, dtype=torch.float32, device=device)
         self._gather, self._reduce = [], None
+        self._views_started = 0
         self.bytes_per_step = {"all_gather_recv": (self.world - 1) * views_local * n_gaussians * 12,
                                "all_reduce_payload": n_gaussians * GEOM_FLOATS * 4,
                                "dense_all_reduce_payload_replaced": n_gaussians * GRAD_FLOATS * 4}
 
-    def start_gather(self, g_rgb: torch.Tensor, campos: torch.Tensor):
-        assert g_rgb.shape == (self.views_local, self.n, 3) and campos.shape == (self.views_local, 3)
+    def start_gather_view(self, c: int, g_view: torch.Tensor, campos: torch.Tensor | None = None):
+        """Asynchronous all-gather of ONE local view's colour gradients [N,3] (and, with the first view, of the camera centres
+        [C_local,3] of the step)."""
+        assert g_view.shape == (self.n, 3)
         if self.world == 1:
-            self.g_all.copy_(g_rgb)
-            self.campos_all.copy_(campos)
-            self._gather = []
-            return
-        self._gather = [dist.all_gather_into_tensor(self.g_all, g_rgb.contiguous(), group=self.group, async_op=True),
-                        dist.all_gather_into_tensor(self.campos_all, campos.contiguous(), group=self.group, async_op=True)]
+            self.g_all[c, 0].copy_(g_view)
+            if campos is not None:
+                self.campos_all[:, 0].copy_(campos)
+        else:
+            self._gather.append(dist.all_gather_into_tensor(self.g_all[c].view(self.world * self.n, 3), g_view.contiguous(),
+                                                            group=self.group, async_op=True))
+            if campos is not None:
+                # [world, C_local, 3] staging -> transposed into the view-major table after the wait
+                self._campos_stage = torch.empty(self.world, self.views_local, 3, dtype=torch.float32, device=g_view.device)
+                self._gather.append(dist.all_gather_into_tensor(self._campos_stage.view(self.world * self.views_local, 3),
+                                                                campos.contiguous(), group=self.group, async_op=True))
+        self._views_started += 1
+
+    def start_gather(self, g_rgb: torch.Tensor, campos: torch.Tensor):
+        """All local views at once (used when the views' gradients become available together, e.g. under autograd)."""
+        assert g_rgb.shape == (self.views_local, self.n, 3) and campos.shape == (self.views_local, 3)
+        for c in range(self.views_local):
+            self.start_gather_view(c, g_rgb[c], campos if c == 0 else None)
+
+    @property
+    def gather_started(self) -> bool:
+        return self._views_started > 0
 
     def wait_gather(self):
+        """Returns (g_all [C_local*world, N, 3], campos_all [C_local*world, 3]) in the same (view-major) order."""
         for w in self._gather:
             w.wait()
+        if self._gather and self.world > 1:
+            self.campos_all.copy_(self._campos_stage.transpose(0, 1))
         self._gather = []
-        return self.g_all, self.campos_all
+        self._views_started = 0
+        return self.g_all.view(-1, self.n, 3), self.campos_all.view(-1, 3)
 
     def start_reduce(self):
         self._reduce = dist.all_reduce(self.geom, group=self.group, async_op=True) if self.world > 1 else None

@@ -321,6 +321,12 @@ class _RasterizeCameras(torch.autograd.Function):
                 None, None)
 
 
+def mask_rgb_grad(splats, v_splats, out):
+    """Colour gradient masked by the SH clamp (rgb = max(.,0): zero gradient where the record's colour is 0); invisible
+    Gaussians have zero accumulators.  ``splats`` / ``v_splats`` [..., N, 12] -> ``out`` [..., N, 3]."""
+    return torch.where(splats[..., 8:11] > 0, v_splats[..., 6:9], v_splats.new_zeros(()), out=out)
+
+
 def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, camposs, W, H, radii, splats, v_splats,
                         out=None, exchange=None):
     """Projection + SH backward for C stacked local views (csrc/raster_project_bwd_multi.cu).
@@ -345,11 +351,14 @@ def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, campo
     # colour gradient masked by the SH clamp (rgb = max(.,0): zero gradient where the record's colour is 0); invisible
     # Gaussians have zero accumulators.  Produced first so that its all-gather overlaps the geometry kernel.
     g_rgb = out.get("g_rgb")
-    if g_rgb is None:
-        g_rgb = torch.empty(Cn, N, 3, dtype=torch.float32, device=dev)
-    torch.where(splats[..., 8:11] > 0, v_splats[..., 6:9], v_splats.new_zeros(()), out=g_rgb)
-    if exchange is not None:
-        exchange.start_gather(g_rgb, Pc)
+    if exchange is not None and getattr(exchange, "gather_started", False):
+        pass                                      # per-view gathers were issued as each view's blend backward finished
+    else:
+        if g_rgb is None:
+            g_rgb = torch.empty(Cn, N, 3, dtype=torch.float32, device=dev)
+        mask_rgb_grad(splats, v_splats, g_rgb)
+        if exchange is not None:
+            exchange.start_gather(g_rgb, Pc)
     _lib.call("adb_raster_project_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(Vc),
               _lib.ptr(Kc), W, H, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(v_splats), _lib.ptr(v_means),
               _lib.ptr(v_quats), _lib.ptr(v_scales), _lib.ptr(v_opac), None, _lib.ptr(v_views), _lib.stream())

@@ -41,7 +41,7 @@ def _worker(rank, world, port, q):
     from artdeco_b200.parallel import GEOM_FLOATS, MultiViewExchange
     Cl = 2
     ex = MultiViewExchange(N, Cl, "cpu")
-    ok &= ex.geom.numel() == N * GEOM_FLOATS == N * 11 and ex.g_all.shape == (world * Cl, N, 3)
+    ok &= ex.geom.numel() == N * GEOM_FLOATS == N * 11 and ex.g_all.shape == (Cl, world, N, 3)
     gr = torch.Generator().manual_seed(100 + rank)
     g_loc, cam_loc = torch.randn(Cl, N, 3, generator=gr), torch.randn(Cl, 3, generator=gr)
     geo_loc = {k: torch.randn(v.shape, generator=gr) for k, v in ex.views.items()}
@@ -58,7 +58,13 @@ def _worker(rank, world, port, q):
         exp_c.append(torch.randn(Cl, 3, generator=g2))
         for k in exp_geo:
             exp_geo[k] += torch.randn(exp_geo[k].shape, generator=g2)
-    ok &= torch.equal(g_all, torch.cat(exp_g)) and torch.equal(cam_all, torch.cat(exp_c))      # rank-major view order
+    # view-major order: entry (c, r) = local view c of rank r, for the gradients and the camera centres alike
+    ok &= torch.equal(g_all, torch.stack(exp_g, 1).reshape(-1, N, 3)) and torch.equal(cam_all, torch.stack(exp_c, 1).reshape(-1, 3))
+    # a second step through the per-view entry point gives the same result (state is reset by wait_gather)
+    for c in range(Cl):
+        ex.start_gather_view(c, g_loc[c], cam_loc if c == 0 else None)
+    g2, c2 = ex.wait_gather()
+    ok &= torch.equal(g2, g_all) and torch.equal(c2, cam_all)
     for k in exp_geo:
         ok &= bool(torch.allclose(ex.views[k], exp_geo[k], atol=1e-6))
     q.put((rank, ok))
