@@ -191,6 +191,20 @@ int adb_adam_update(long long N, long long M, float* param, const float* grad, f
 int adb_lod_select_workspace_bytes(long long N, size_t* bytes /*HOST*/);
 int adb_lod_select(long long N, const float* xyz, const float* d_max, const float* cam /*[3]*/, unsigned char* mask,
                    float* ratio, int32_t* ids, int32_t* count, void* ws, size_t ws_bytes, adb_stream_t stream);
+/* Global Gauss-Newton over Sim(3) key-frame poses: mast3r_slam_backends.gauss_newton_rays / gauss_newton_calib
+ * (VSLAM/backend/src/gn.cpp:32-82, gn_kernels.cu:813-1637; callers VSLAM/mast3r_slam/global_opt.py:158,208).
+ * mode 0 = rays (sigma_a = sigma_ray, sigma_b = sigma_dist), mode 1 = calib (sigma_a = sigma_pixel, sigma_b = sigma_depth; K3x3 =
+ * device pointer to the row-major intrinsics).  poses [K,8] (t, q xyzw, s) updated IN PLACE, pose 0 fixed; Xs [K,n,3]; Cs [K,n];
+ * ii / jj int64 [E] = positions of the edge's key frames in the pose table; idx_ii2jj int64 [E,n]; valid_match bool [E,n];
+ * Q [E,n].  dx_out [K-1,7] = last step; state_out int32[4] on the device = {iterations run, converged, |dx| (float bits),
+ * last Cholesky ok}.  The whole solve (normal equations, dense double Cholesky, retraction, termination test) runs on the
+ * device: no host sync.  ws from adb_gn_workspace_bytes. */
+int adb_gn_workspace_bytes(int n_poses, int n_edges, size_t* bytes /*HOST*/);
+int adb_gauss_newton(int mode, int n_poses, int n_pts, int n_edges, float* poses, const float* Xs, const float* Cs,
+                     const float* K3x3, const long long* ii, const long long* jj, const long long* idx_ii2jj,
+                     const unsigned char* valid_match, const float* Q, int height, int width, int pixel_border, float z_eps,
+                     float sigma_a, float sigma_b, float C_thresh, float Q_thresh, int max_iter, float delta_thresh,
+                     float* dx_out, int* state_out, void* ws, size_t ws_bytes, adb_stream_t stream);
 /* update_voxel (Reconstruct/scene/scene_models/h3dgsv3.py:227-316): voxel-hash class ids without the reference's three sorts
  * (csrc/voxel.cu).  Tables are caller-allocated: vkeys[V], pkeys[P], ukeys[U] uint64 pre-filled with 0xFF bytes; pcount[P]
  * int32 and best[V] uint64 zeroed; V, P powers of two >= 2N, U >= 2M.  mn = device float[3] minimum over all points.

@@ -1,14 +1,15 @@
-"""Drop-in for the reference's ``mast3r_slam_backends`` extension (VSLAM/backend/src/gn.cpp:84-112).
+"""Drop-in for the reference's ``mast3r_slam_backends`` extension (VSLAM/backend/src/gn.cpp:84-122).
 
-``iter_proj`` and ``refine_matches`` are served by artdeco_b200's kernels.  Every other attribute (the Gauss-Newton entry
-points ``gauss_newton_points / _rays / _calib`` that VSLAM/mast3r_slam/global_opt.py calls) is DELEGATED to the reference's own
-compiled extension when one is importable further down ``sys.path`` — putting ``shims/`` first must not take the SLAM
-pipeline's global optimisation away.  Only when no real extension exists does the lookup fail, loudly."""
+``iter_proj``, ``refine_matches``, ``gauss_newton_rays`` and ``gauss_newton_calib`` (everything ARTDECO calls:
+VSLAM/utils_matching.py, VSLAM/mast3r_slam/global_opt.py:158,208) are served by artdeco_b200's kernels.  Any other attribute
+(``gauss_newton_points``, which ARTDECO never calls) is DELEGATED to the reference's own compiled extension when one is
+importable further down ``sys.path``; only when none exists does the lookup fail, loudly."""
 import importlib.machinery
 import importlib.util
 import os
 import sys
 
+from artdeco_b200.gn import gauss_newton_calib, gauss_newton_rays  # noqa: F401
 from artdeco_b200.matching import iter_proj, refine_matches  # noqa: F401
 
 _HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -42,6 +43,7 @@ def __getattr__(name):
     if real is not None and hasattr(real, name):
         return getattr(real, name)
     if name.startswith("gauss_newton"):
-        raise NotImplementedError(f"mast3r_slam_backends.{name}: artdeco_b200 serves iter_proj / refine_matches only and no "
-                                  "compiled reference extension was found on sys.path to delegate the Gauss-Newton solver to")
+        raise NotImplementedError(f"mast3r_slam_backends.{name}: artdeco_b200 serves iter_proj / refine_matches / "
+                                  "gauss_newton_rays / gauss_newton_calib; no compiled reference extension was found on "
+                                  "sys.path to delegate this entry point to")
     raise AttributeError(name)

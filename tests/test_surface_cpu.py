@@ -18,7 +18,7 @@ SHIMS = {
                                     "rasterize_gaussians"],                           # optimizers.py:14, webviewer/scene_models.py:33-36
     "gsplat.rendering": ["rasterization"],                                           # h3dgsv3.py:664
     "curope": ["rope_2d", "cuRoPE2D"],                                               # curope2d.py:7-10
-    "mast3r_slam_backends": ["iter_proj", "refine_matches"],                         # utils_matching.py:3
+    "mast3r_slam_backends": ["iter_proj", "refine_matches", "gauss_newton_rays", "gauss_newton_calib"],                         # utils_matching.py:3
 }
 
 
@@ -41,7 +41,7 @@ def test_shims_expose_the_reference_names(shims_on_path):
             assert hasattr(m, n), f"{mod}.{n}"
     import mast3r_slam_backends as b
     with pytest.raises(NotImplementedError):
-        b.gauss_newton_rays  # noqa: B018  (out of scope: must say so, not AttributeError)
+        b.gauss_newton_points  # noqa: B018  (ARTDECO never calls it: delegated, or a loud refusal — not AttributeError)
     s = importlib.import_module("diff_gaussian_rasterization").GaussianRasterizationSettings(
         4, 6, 0.5, 0.5, torch.zeros(3), 1.0, torch.eye(4), 3, torch.zeros(3), False, False)
     assert s.image_height == 4 and s.image_width == 6 and s.sh_degree == 3      # positional order of webviewer/scene_models.py:559-571
@@ -50,13 +50,13 @@ def test_shims_expose_the_reference_names(shims_on_path):
 def test_backend_shim_delegates_gauss_newton_to_a_real_extension(shims_on_path, tmp_path):
     """with shims/ first on sys.path the Gauss-Newton entry points must still reach the reference's compiled
     extension further down the path (here: a stand-in module)."""
-    (tmp_path / "mast3r_slam_backends.py").write_text("def gauss_newton_rays(*a):\n    return ('real', len(a))\n")
+    (tmp_path / "mast3r_slam_backends.py").write_text("def gauss_newton_points(*a):\n    return ('real', len(a))\n")
     sys.path.append(str(tmp_path))
     try:
         sys.modules.pop("mast3r_slam_backends", None)
         b = importlib.import_module("mast3r_slam_backends")
-        assert b.gauss_newton_rays(1, 2, 3) == ("real", 3)
-        assert b.iter_proj.__module__.startswith("artdeco_b200")       # ours still wins for the matching half
+        assert b.gauss_newton_points(1, 2, 3) == ("real", 3)
+        assert b.iter_proj.__module__.startswith("artdeco_b200") and b.gauss_newton_rays.__module__.startswith("artdeco_b200")
     finally:
         sys.path.remove(str(tmp_path))
         sys.modules.pop("mast3r_slam_backends", None)
