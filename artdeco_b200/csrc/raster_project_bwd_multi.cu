@@ -259,7 +259,8 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
 __global__ void __launch_bounds__(PB)
 sh_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* __restrict__ sh, int sh_degree,
                     const float* __restrict__ campos, const float* __restrict__ g_rgb, float* __restrict__ v_sh,
-                    float* __restrict__ v_means, int accumulate, float* __restrict__ v_campos) {
+                    float* __restrict__ v_means, int accumulate, int skip_mod, int skip_val,
+                    float* __restrict__ v_campos) {
     __shared__ float sRed[PB / 32][3];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < N;
@@ -274,6 +275,14 @@ sh_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* 
         for (int k = 0; k < 12; ++k) {
             const float4 q = adb_ldg_stream4(sp + k);
             c48[4 * k] = q.x; c48[4 * k + 1] = q.y; c48[4 * k + 2] = q.z; c48[4 * k + 3] = q.w;
+        }
+        if (accumulate & 2) {            // second pass of a split expansion: continue from the stored partial sums
+            const float4* op0 = reinterpret_cast<const float4*>(v_sh + (size_t)i * 48);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const float4 q = op0[k];
+                o48[4 * k] = q.x; o48[4 * k + 1] = q.y; o48[4 * k + 2] = q.z; o48[4 * k + 3] = q.w;
+            }
         }
     }
     float gm[3] = {0.f, 0.f, 0.f};
@@ -292,7 +301,8 @@ sh_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* 
             const float* gp = g_rgb + ((size_t)(c + 1) * N + i) * 3;
             gn[0] = gp[0]; gn[1] = gp[1]; gn[2] = gp[2];
         }
-        if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {
+        const bool skip = skip_mod > 0 && (c % skip_mod) == skip_val;     // views already expanded by the first pass
+        if (!skip && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f)) {
             const float dx = mu[0] - campos[3 * c], dy = mu[1] - campos[3 * c + 1], dz = mu[2] - campos[3 * c + 2];
             const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
             const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
@@ -300,13 +310,14 @@ sh_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* 
             sh_basis_grad(sh_degree, nx, ny, nz, Bs, Bx, By, Bz);
             float vnx = 0.f, vny = 0.f, vnz = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float sv = c48[3 * k + ch] * g[ch];
-                    o48[3 * k + ch] = fmaf(Bs[k], g[ch], o48[3 * k + ch]);
-                    vnx += Bx[k] * sv; vny += By[k] * sv; vnz += Bz[k] * sv;
-                }
+            for (int k = 0; k < 16; ++k) {
+                // s_k = <coefficients of band k, g>: one dot product feeds the three direction-gradient sums
+                const float sk = fmaf(c48[3 * k], g[0], fmaf(c48[3 * k + 1], g[1], c48[3 * k + 2] * g[2]));
+                vnx = fmaf(Bx[k], sk, vnx); vny = fmaf(By[k], sk, vny); vnz = fmaf(Bz[k], sk, vnz);
+                o48[3 * k] = fmaf(Bs[k], g[0], o48[3 * k]);
+                o48[3 * k + 1] = fmaf(Bs[k], g[1], o48[3 * k + 1]);
+                o48[3 * k + 2] = fmaf(Bs[k], g[2], o48[3 * k + 2]);
+            }
             const float dot = vnx * nx + vny * ny + vnz * nz;
             const float gx = (vnx - dot * nx) * inv, gy = (vny - dot * ny) * inv, gz = (vnz - dot * nz) * inv;
             gm[0] += gx; gm[1] += gy; gm[2] += gz;
@@ -331,8 +342,8 @@ sh_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* 
     float4* op = reinterpret_cast<float4*>(v_sh + (size_t)i * 48);
 #pragma unroll
     for (int k = 0; k < 12; ++k) op[k] = make_float4(o48[4 * k], o48[4 * k + 1], o48[4 * k + 2], o48[4 * k + 3]);
-    if (accumulate) { v_means[3 * i] += gm[0]; v_means[3 * i + 1] += gm[1]; v_means[3 * i + 2] += gm[2]; }
-    else            { v_means[3 * i] = gm[0];  v_means[3 * i + 1] = gm[1];  v_means[3 * i + 2] = gm[2]; }
+    if (accumulate & 1) { v_means[3 * i] += gm[0]; v_means[3 * i + 1] += gm[1]; v_means[3 * i + 2] += gm[2]; }
+    else                { v_means[3 * i] = gm[0];  v_means[3 * i + 1] = gm[1];  v_means[3 * i + 2] = gm[2]; }
 }
 
 }  // namespace
@@ -358,18 +369,20 @@ ADB_API int adb_raster_project_bwd_multi(int N, int C, const float* means, const
     return ADB_OK;
 }
 
-// v_sh [N,48] OVERWRITTEN with sum_c basis(dir_c) (x) g_rgb[c]; the direction term is added to v_means [N,3]
-// (accumulate != 0) or written to it (accumulate == 0: a separate buffer, so that an all-reduce of the geometry gradients can
-// be in flight meanwhile); v_campos [C,3] (may be NULL) accumulated.  g_rgb may hold views rendered on OTHER GPUs
-// (all-gathered): only their campos[C,3] is needed.
+// v_sh [N,48] = sum_c basis(dir_c) (x) g_rgb[c]; the direction term goes to v_means [N,3].  accumulate bit 0: v_means += (else
+// =: a separate buffer, so that an all-reduce of the geometry gradients can be in flight meanwhile); bit 1: v_sh += (else =).
+// skip_mod > 0 skips the views c with c % skip_mod == skip_val — the second pass of a split expansion (multi-GPU: the local
+// views are expanded while the other ranks' colour gradients are still being gathered; in the view-major gathered table
+// [C_local, world] the local entries are those with c % world == rank).  v_campos [C,3] (may be NULL) accumulated.  g_rgb
+// may hold views rendered on OTHER GPUs: only their campos[C,3] is needed.
 ADB_API int adb_raster_sh_bwd_multi(int N, int C, const float* means, const float* sh, int sh_degree,
                                     const float* campos, const float* g_rgb, float* v_sh, float* v_means,
-                                    int accumulate, float* v_campos, cudaStream_t stream) {
+                                    int accumulate, int skip_mod, int skip_val, float* v_campos, cudaStream_t stream) {
     ADB_REQUIRE(N >= 0 && C >= 1 && sh_degree >= 0 && sh_degree <= 3, "adb_raster_sh_bwd_multi: bad sizes");
     if (N == 0) return ADB_OK;
     ADB_REQUIRE(means && sh && campos && g_rgb && v_sh && v_means, "adb_raster_sh_bwd_multi: null pointer");
     sh_bwd_multi_kernel<<<adb_cdiv(N, PB), PB, 0, stream>>>(N, C, means, sh, sh_degree, campos, g_rgb, v_sh, v_means,
-                                                           accumulate, v_campos);
+                                                           accumulate, skip_mod, skip_val, v_campos);
     ADB_CHECK_LAUNCH("sh_bwd_multi_kernel");
     return ADB_OK;
 }

@@ -57,6 +57,7 @@ class MultiViewExchange:
         self.n = n_gaussians
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.views_local = views_local
         self.geom = torch.zeros(n_gaussians * GEOM_FLOATS, dtype=torch.float32, device=device)
         self.views = {}

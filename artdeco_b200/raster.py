@@ -33,7 +33,7 @@ _lib.register("adb_raster_project_bwd", [i32, vp, vp, vp, vp, i32, vp, vp, vp, i
                                          vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 
 _lib.register("adb_raster_project_bwd_multi", [i32, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
-_lib.register("adb_raster_sh_bwd_multi", [i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp])
+_lib.register("adb_raster_sh_bwd_multi", [i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp])
 
 _lib.register("adb_raster_project_fwd_legacy", [i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32,
                                                 vp, vp, vp, vp])
@@ -364,13 +364,21 @@ def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, campo
               _lib.ptr(v_quats), _lib.ptr(v_scales), _lib.ptr(v_opac), None, _lib.ptr(v_views), _lib.stream())
     if exchange is None:
         _lib.call("adb_raster_sh_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(sh), int(sh_degree), _lib.ptr(Pc),
-                  _lib.ptr(g_rgb), _lib.ptr(v_sh), _lib.ptr(v_means), 1, _lib.ptr(v_campos), _lib.stream())
+                  _lib.ptr(g_rgb), _lib.ptr(v_sh), _lib.ptr(v_means), 1, 0, 0, _lib.ptr(v_campos), _lib.stream())
         return v_means, v_quats, v_scales, v_opac, v_sh, v_views, v_campos
     exchange.start_reduce()                       # geometry bucket (v_means | v_quats | v_scales | v_opac live in it)
-    g_all, P_all = exchange.wait_gather()
     v_means_sh = exchange.scratch_means
+    split = getattr(exchange, "world", 1) > 1 and getattr(exchange, "rank", None) is not None and out.get("g_rgb") is not None
+    if split:
+        # the LOCAL views' colour gradients are expanded while the other ranks' are still being gathered ...
+        g_loc = out["g_rgb"]
+        _lib.call("adb_raster_sh_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(sh), int(sh_degree), _lib.ptr(Pc), _lib.ptr(g_loc),
+                  _lib.ptr(v_sh), _lib.ptr(v_means_sh), 0, 0, 0, None, _lib.stream())
+    g_all, P_all = exchange.wait_gather()
+    # ... then every other rank's views are added (view-major table: entry c belongs to rank c % world)
     _lib.call("adb_raster_sh_bwd_multi", N, int(g_all.shape[0]), _lib.ptr(means), _lib.ptr(sh), int(sh_degree),
-              _lib.ptr(P_all), _lib.ptr(g_all), _lib.ptr(v_sh), _lib.ptr(v_means_sh), 0, None, _lib.stream())
+              _lib.ptr(P_all), _lib.ptr(g_all), _lib.ptr(v_sh), _lib.ptr(v_means_sh), 3 if split else 0,
+              exchange.world if split else 0, exchange.rank if split else 0, None, _lib.stream())
     exchange.wait_reduce()
     v_means.add_(v_means_sh)
     return v_means, v_quats, v_scales, v_opac, v_sh, v_views, v_campos

@@ -70,7 +70,8 @@ int adb_raster_project_bwd_multi(int N, int C, const float* means, const float* 
                                  const float* splats, const float* v_splats, float* v_means, float* v_quats, float* v_scales,
                                  float* v_opac, float* g_rgb, float* v_viewmats, adb_stream_t stream);
 int adb_raster_sh_bwd_multi(int N, int C, const float* means, const float* sh, int sh_degree, const float* campos,
-                            const float* g_rgb, float* v_sh, float* v_means, int accumulate /* 0: v_means = term */,
+                            const float* g_rgb, float* v_sh, float* v_means, int accumulate /* bit0: v_means +=, bit1: v_sh += */,
+                            int skip_mod, int skip_val /* skip views c % skip_mod == skip_val when skip_mod > 0 */,
                             float* v_campos, adb_stream_t stream);
 /* Tile-bucketed intersection (no library sort, no host sync; bit-identical to adb_raster_isect_emit + adb_raster_sort +
  * adb_raster_tile_offsets, i.e. to gsplat's isect_tiles / radix sort / isect_offset_encode behind h3dgsv3.py:664-680):

@@ -248,10 +248,21 @@ def test_multi_view_exchange_algebra_matches_single_process(cuda):
     v_means_sh = torch.empty(N, 3, device=cuda)
     from artdeco_b200 import _lib
     _lib.call("adb_raster_sh_bwd_multi", N, 4, _lib.ptr(t["means"]), _lib.ptr(t["sh"]), 3, _lib.ptr(p_all), _lib.ptr(g_all),
-              _lib.ptr(v_sh), _lib.ptr(v_means_sh), 0, None, _lib.stream())
+              _lib.ptr(v_sh), _lib.ptr(v_means_sh), 0, 0, 0, None, _lib.stream())
     assert rel_err(geo[0] + v_means_sh, full[0]) < 2e-5, "v_means"
     assert rel_err(geo[1], full[1]) < 2e-5 and rel_err(geo[2], full[2]) < 2e-5 and rel_err(geo[3], full[3]) < 2e-5
     assert rel_err(v_sh, full[4]) < 2e-5, "v_sh expanded from gathered colour gradients"
+    # split expansion used on multi-GPU runs: "rank 0" expands its local views (0,1) first, then adds the others from the
+    # view-major gathered table [C_local, world] (entry c belongs to rank c % world) with its own entries skipped
+    world, rank = 2, 0
+    g_vm = torch.stack([torch.stack([parts[r][0][c] for r in range(world)]) for c in range(2)]).reshape(4, N, 3).contiguous()
+    p_vm = torch.stack([torch.stack([parts[r][1][c] for r in range(world)]) for c in range(2)]).reshape(4, 3).contiguous()
+    v_sh2, v_ms2 = torch.empty(N, 16, 3, device=cuda), torch.empty(N, 3, device=cuda)
+    _lib.call("adb_raster_sh_bwd_multi", N, 2, _lib.ptr(t["means"]), _lib.ptr(t["sh"]), 3, _lib.ptr(parts[rank][1].contiguous()),
+              _lib.ptr(parts[rank][0].contiguous()), _lib.ptr(v_sh2), _lib.ptr(v_ms2), 0, 0, 0, None, _lib.stream())
+    _lib.call("adb_raster_sh_bwd_multi", N, 4, _lib.ptr(t["means"]), _lib.ptr(t["sh"]), 3, _lib.ptr(p_vm), _lib.ptr(g_vm),
+              _lib.ptr(v_sh2), _lib.ptr(v_ms2), 3, world, rank, None, _lib.stream())
+    assert rel_err(v_sh2, v_sh) < 1e-5 and rel_err(v_ms2, v_means_sh) < 1e-5, "split (local first, then remote) == one pass"
 
 
 @pytest.mark.gpu
