@@ -475,11 +475,11 @@ tile_sort_kernel(int T, const int32_t* __restrict__ offsets, u64* __restrict__ p
 // and flagged.
 static int tile_bucket_impl(int convention, int N, const int32_t* radii, const float* splats,
                             const int32_t* tiles_per_gauss, int W, int H, long long capacity, int32_t* tile_counts,
-                            int32_t* tile_offsets, long long* total, int32_t* overflow, cudaStream_t stream) {
+                            int32_t* tile_offsets, long long* total, int32_t* overflow, int counts_ready, cudaStream_t stream) {
     ADB_REQUIRE(N >= 0 && W > 0 && H > 0 && capacity >= 0 && capacity < 2147483647LL, "adb_raster_tile_count_scan: bad sizes");
     ADB_REQUIRE(tile_counts && tile_offsets, "adb_raster_tile_count_scan: null pointer");
     const int T = adb_cdiv(W, ADB_TILE) * adb_cdiv(H, ADB_TILE);
-    if (N > 0) {
+    if (N > 0 && !counts_ready) {
         ADB_REQUIRE(radii && splats && tiles_per_gauss, "adb_raster_tile_count_scan: null pointer");
         tile_count_kernel<<<adb_cdiv(N, 256), 256, 0, stream>>>(N, radii, splats, tiles_per_gauss, W, H, convention,
                                                                tile_counts);
@@ -495,7 +495,14 @@ ADB_API int adb_raster_tile_count_scan(int N, const int32_t* radii, const float*
                                        int W, int H, int legacy, long long capacity, int32_t* tile_counts,
                                        int32_t* tile_offsets, long long* total, int32_t* overflow, cudaStream_t stream) {
     return tile_bucket_impl(legacy ? ADB_CONV_INRIA : ADB_CONV_GSPLAT, N, radii, splats, tiles_per_gauss, W, H, capacity,
-                            tile_counts, tile_offsets, total, overflow, stream);
+                            tile_counts, tile_offsets, total, overflow, 0, stream);
+}
+
+// Scan only: the counters were filled by adb_raster_project_fwd_counts.
+ADB_API int adb_raster_tile_scan(int W, int H, long long capacity, int32_t* tile_counts, int32_t* tile_offsets,
+                                 long long* total, int32_t* overflow, cudaStream_t stream) {
+    return tile_bucket_impl(ADB_CONV_GSPLAT, 0, nullptr, nullptr, nullptr, W, H, capacity, tile_counts, tile_offsets, total,
+                            overflow, 1, stream);
 }
 
 // Scatter + per-tile sort.  keys [capacity] int64, vals [capacity] int32, packed [capacity] uint64 scratch; tile_counts as

@@ -48,9 +48,11 @@ __global__ void __launch_bounds__(256)
 project_fwd_kernel(int N, const float* __restrict__ means, const float* __restrict__ quats,
                    const float* __restrict__ scales, const float* __restrict__ opacities,
                    const float* __restrict__ sh, int sh_degree, AdbCam cam,
-                   int32_t* __restrict__ radii, float* __restrict__ splats, int32_t* __restrict__ tiles_per_gauss) {
+                   int32_t* __restrict__ radii, float* __restrict__ splats, int32_t* __restrict__ tiles_per_gauss,
+                   int32_t* __restrict__ tile_counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    int tr_x0 = 0, tr_x1 = 0, tr_y0 = 0, tr_y1 = 0;    // tile rectangle (for the fused per-tile counting)
     const float* V = cam.viewmat;
     const float R[9] = {V[0], V[1], V[2], V[4], V[5], V[6], V[8], V[9], V[10]};
     const float t[3] = {V[3], V[7], V[11]};
@@ -117,6 +119,7 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
                 int x0, x1, y0, y1;
                 adb_tile_rect(u, v, rI, rI, cam.W, cam.H, ADB_CONV_INRIA, x0, x1, y0, y1);
                 count = (x1 - x0) * (y1 - y0);
+                tr_x0 = x0; tr_x1 = x1; tr_y0 = y0; tr_y1 = y1;
                 ok = count > 0;          // Inria leaves radii = 0 when no tile is touched
                 if (ok) {
                     rx_i = ry_i = rI;
@@ -158,12 +161,21 @@ project_fwd_kernel(int N, const float* __restrict__ means, const float* __restri
                 int x0, x1, y0, y1;
                 adb_tile_rect(u, v, rx_i, ry_i, cam.W, cam.H, ADB_CONV_GSPLAT, x0, x1, y0, y1);
                 count = (x1 - x0) * (y1 - y0);
+                tr_x0 = x0; tr_x1 = x1; tr_y0 = y0; tr_y1 = y1;
             }
         }
         }
     }
     reinterpret_cast<int2*>(radii)[i] = make_int2(rx_i, ry_i);
     tiles_per_gauss[i] = count;
+    if (tile_counts && count > 0) {
+        // fused first stage of the tile-bucketed intersection (raster_isect.cu): fire-and-forget REDs into the replicated
+        // per-tile counters, overlapped with the SH loads below instead of a separate pass over radii / means2d
+        const int tw = (cam.W + ADB_TILE - 1) / ADB_TILE;
+        const int cp = blockIdx.x & (ADB_TILE_COUNTER_COPIES - 1);
+        for (int ty = tr_y0; ty < tr_y1; ++ty)
+            for (int tx = tr_x0; tx < tr_x1; ++tx) atomicAdd(tile_counts + (ty * tw + tx) * ADB_TILE_COUNTER_COPIES + cp, 1);
+    }
     if (!ok) return;
 
     float r = 0.f, g = 0.f, bl = 0.f;
@@ -201,7 +213,8 @@ static int project_fwd_impl(int convention, int N, const float* means, const flo
                             const float* opacities, const float* sh, int sh_degree,
                             const float* viewmat, const float* K, const float* campos, int W, int H,
                             float eps2d, float near_plane, float far_plane, float radius_clip,
-                            int32_t* radii, float* splats, int32_t* tiles_per_gauss, cudaStream_t stream) {
+                            int32_t* radii, float* splats, int32_t* tiles_per_gauss, int32_t* tile_counts,
+                            cudaStream_t stream) {
     ADB_REQUIRE(N >= 0 && W > 0 && H > 0, "adb_raster_project_fwd: bad sizes");
     if (N == 0) return ADB_OK;
     ADB_REQUIRE(means && quats && scales && opacities && viewmat && K && radii && splats && tiles_per_gauss,
@@ -210,7 +223,7 @@ static int project_fwd_impl(int convention, int N, const float* means, const flo
     ADB_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "adb_raster_project_fwd: sh_degree must be 0..3");
     AdbCam cam{viewmat, K, campos, W, H, eps2d, near_plane, far_plane, radius_clip, convention};
     project_fwd_kernel<<<adb_cdiv(N, 256), 256, 0, stream>>>(N, means, quats, scales, opacities, sh, sh_degree, cam,
-                                                            radii, splats, tiles_per_gauss);
+                                                            radii, splats, tiles_per_gauss, tile_counts);
     ADB_CHECK_LAUNCH("project_fwd_kernel");
     return ADB_OK;
 }
@@ -221,7 +234,20 @@ ADB_API int adb_raster_project_fwd(int N, const float* means, const float* quats
                                    float eps2d, float near_plane, float far_plane, float radius_clip,
                                    int32_t* radii, float* splats, int32_t* tiles_per_gauss, cudaStream_t stream) {
     return project_fwd_impl(ADB_CONV_GSPLAT, N, means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H,
-                            eps2d, near_plane, far_plane, radius_clip, radii, splats, tiles_per_gauss, stream);
+                            eps2d, near_plane, far_plane, radius_clip, radii, splats, tiles_per_gauss, nullptr, stream);
+}
+
+// Same, plus the first stage of the tile-bucketed intersection fused in: tile_counts (int32 [2*4*T], first half zero on entry,
+// see adb_raster_tile_count_scan) receives one RED per (Gaussian, touched tile); pass counts_ready = 1 to the scan afterwards.
+ADB_API int adb_raster_project_fwd_counts(int N, const float* means, const float* quats, const float* scales,
+                                          const float* opacities, const float* sh, int sh_degree,
+                                          const float* viewmat, const float* K, const float* campos, int W, int H,
+                                          float eps2d, float near_plane, float far_plane, float radius_clip,
+                                          int32_t* radii, float* splats, int32_t* tiles_per_gauss, int32_t* tile_counts,
+                                          cudaStream_t stream) {
+    ADB_REQUIRE(tile_counts, "adb_raster_project_fwd_counts: null tile_counts");
+    return project_fwd_impl(ADB_CONV_GSPLAT, N, means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H,
+                            eps2d, near_plane, far_plane, radius_clip, radii, splats, tiles_per_gauss, tile_counts, stream);
 }
 
 // Legacy (Inria / diff_gaussian_rasterization) conventions: radii[:,0] == radii[:,1] == ceil(3 sqrt(lambda_max)); the
@@ -232,5 +258,5 @@ ADB_API int adb_raster_project_fwd_legacy(int N, const float* means, const float
                                           float eps2d, float near_plane, float far_plane,
                                           int32_t* radii, float* splats, int32_t* tiles_per_gauss, cudaStream_t stream) {
     return project_fwd_impl(ADB_CONV_INRIA, N, means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H,
-                            eps2d, near_plane, far_plane, 0.f, radii, splats, tiles_per_gauss, stream);
+                            eps2d, near_plane, far_plane, 0.f, radii, splats, tiles_per_gauss, nullptr, stream);
 }

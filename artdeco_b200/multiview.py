@@ -75,10 +75,11 @@ class MultiViewStep:
         sh_degree, eps2d, near, far, rclip = self.cfg
         p, W, H, N = self.p, self.W, self.H, self.N
         self.v_splats[c].zero_()
+        cnt = R.new_tile_counts(W, H, self.dev)        # per-tile counting is fused into the projection kernel
         R.project(p["means"], p["quats"], p["scales"], p["opacities"], p["sh"], sh_degree, self.V[c], self.K[c], self.P[c],
-                  W, H, eps2d, near, far, rclip, out=(self.radii[c], self.splats[c], self.tpg[c]))
+                  W, H, eps2d, near, far, rclip, out=(self.radii[c], self.splats[c], self.tpg[c]), tile_counts=cnt)
         cap = None if capacity is None else capacity[c]
-        keys, vals, offs, info = R.intersect(self.radii[c], self.splats[c], self.tpg[c], W, H, capacity=cap)
+        keys, vals, offs, info = R.intersect(self.radii[c], self.splats[c], self.tpg[c], W, H, capacity=cap, counts=cnt)
         col, alp, last = R.blend_forward(W, H, N, self.splats[c], vals, offs)
         R.blend_backward(W, H, N, self.splats[c], vals, offs, alp, last, self.v_colors[c], self.v_alphas[c],
                          out=self.v_splats[c])

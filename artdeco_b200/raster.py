@@ -19,6 +19,9 @@ from ._lib import f32, i32, i64, vp
 
 _lib.register("adb_raster_project_fwd", [i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32,
                                          vp, vp, vp, vp])
+_lib.register("adb_raster_project_fwd_counts", [i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32,
+                                                vp, vp, vp, vp, vp])
+_lib.register("adb_raster_tile_scan", [i32, i32, i64, vp, vp, vp, vp, vp])
 _lib.register("adb_raster_scan_workspace_bytes", [i32, C.POINTER(C.c_size_t)])
 _lib.register("adb_raster_isect_scan", [i32, vp, vp, vp, C.c_size_t, vp])
 _lib.register("adb_raster_isect_emit", [i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp])
@@ -65,10 +68,12 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H, eps2d, near, far, radius_clip,
-            legacy=False, out=None):
+            legacy=False, out=None, tile_counts=None):
     """Projection + SH + tile counts for one camera.  Returns radii[N,2] i32, splats[N,12], tiles_per_gauss[N].
     ``legacy``: Inria conventions (see include/artdeco_b200.h, adb_raster_project_fwd_legacy).
-    ``out``: optional preallocated (radii, splats, tpg) — slices of per-camera stacks in the multi-view path."""
+    ``out``: optional preallocated (radii, splats, tpg) — slices of per-camera stacks in the multi-view path.
+    ``tile_counts``: optional zeroed counter buffer from ``new_tile_counts``: the per-tile counting of the bucketed
+    intersection is fused into the projection kernel (pass the same buffer to ``intersect(counts=...)``)."""
     N = means.shape[0]
     dev = means.device
     if out is not None:
@@ -82,13 +87,24 @@ def project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, 
                   _lib.ptr(opacities), _lib.ptr(sh), int(sh_degree), _lib.ptr(viewmat), _lib.ptr(K), _lib.ptr(campos),
                   W, H, eps2d, near, far, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), _lib.stream())
         return radii, splats, tpg
+    if tile_counts is not None:
+        _lib.call("adb_raster_project_fwd_counts", N, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
+                  _lib.ptr(sh), int(sh_degree), _lib.ptr(viewmat), _lib.ptr(K), _lib.ptr(campos), W, H, eps2d, near, far,
+                  radius_clip, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), _lib.ptr(tile_counts), _lib.stream())
+        return radii, splats, tpg
     _lib.call("adb_raster_project_fwd", N, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(opacities),
               _lib.ptr(sh), int(sh_degree), _lib.ptr(viewmat), _lib.ptr(K), _lib.ptr(campos), W, H, eps2d, near, far,
               radius_clip, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), _lib.stream())
     return radii, splats, tpg
 
 
-def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=False, capacity=None, method=None):
+def new_tile_counts(W, H, dev):
+    """Zeroed counter buffer of the tile-bucketed intersection: 4 replicated counters per tile, then their segment starts."""
+    T = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
+    return torch.zeros(2 * COUNTER_COPIES * T, dtype=torch.int32, device=dev)
+
+
+def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=False, capacity=None, method=None, counts=None):
     """Tile keys/values (sorted), tile offsets [T+1] for one camera.
 
     ``method="bucket"`` (default): tile-bucketed pipeline — count, scan, scatter, one CTA-local bitonic sort per tile
@@ -100,7 +116,8 @@ def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=Fa
     ``capacity=int``: NO host sync (CUDA-graph capturable): buffers hold ``capacity`` intersections, the true count and an
     overflow flag stay on the device; returns ``(keys[capacity], vals[capacity], offsets, info)`` with
     ``info = {"n_isect": int64[1] tensor, "overflow": int32[1] tensor}``; entries beyond ``offsets[T]`` are undefined.  On
-    overflow the dropped intersections make the image wrong but nothing is written out of bounds."""
+    overflow the dropped intersections make the image wrong but nothing is written out of bounds.
+    ``counts``: the buffer ``project(..., tile_counts=...)`` filled (counting fused into the projection): only the scan runs."""
     N = radii.shape[0]
     dev = radii.device
     T = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
@@ -117,12 +134,16 @@ def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=Fa
         return e64, e32, offsets, {"n_isect": torch.zeros(1, dtype=torch.int64, device=dev),
                                    "overflow": torch.zeros(1, dtype=torch.int32, device=dev)}
     if method == "bucket" and sort:
-        counts = torch.zeros(2 * COUNTER_COPIES * T, dtype=torch.int32, device=dev)   # counters | segment starts
         total = torch.zeros(1, dtype=torch.int64, device=dev)
         overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         cap_scan = int(capacity) if capacity is not None else 2147483646
-        _lib.call("adb_raster_tile_count_scan", N, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), W, H, int(legacy),
-                  cap_scan, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(total), _lib.ptr(overflow), _lib.stream())
+        if counts is not None:
+            _lib.call("adb_raster_tile_scan", W, H, cap_scan, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(total),
+                      _lib.ptr(overflow), _lib.stream())
+        else:
+            counts = torch.zeros(2 * COUNTER_COPIES * T, dtype=torch.int32, device=dev)   # counters | segment starts
+            _lib.call("adb_raster_tile_count_scan", N, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(tpg), W, H, int(legacy),
+                      cap_scan, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(total), _lib.ptr(overflow), _lib.stream())
         if capacity is None:
             n_isect = int(total.item())      # the pipeline's single host sync
             if n_isect >= 2147483647:
@@ -206,11 +227,12 @@ class _RasterizeOneCamera(torch.autograd.Function):
         _lib.require_cuda(means)
         N = means.shape[0]
         with torch.cuda.device(means.device):
+            cnt = new_tile_counts(W, H, means.device) if N > 0 else None
             radii, splats, tpg = project(means, quats, scales, opacities, sh, sh_degree, viewmat, K, campos, W, H,
-                                         eps2d, near, far, radius_clip)
+                                         eps2d, near, far, radius_clip, tile_counts=cnt)
             if colors_direct is not None:
                 splats[:, 8:11] = colors_direct
-            keys, vals, offsets, n_isect = intersect(radii, splats, tpg, W, H, cam_id, n_cams)
+            keys, vals, offsets, n_isect = intersect(radii, splats, tpg, W, H, cam_id, n_cams, counts=cnt)
             colors, alphas, last_ids = blend_forward(W, H, N, splats, vals, offsets)
         ctx.save_for_backward(means, quats, scales, opacities, sh, viewmat, K, campos, radii, splats, vals, offsets,
                               alphas, last_ids)
@@ -271,10 +293,11 @@ class _RasterizeCameras(torch.autograd.Function):
             last_ids = torch.empty(Cn, H, W, dtype=torch.int32, device=dev)
             keys_l, vals_l, offs_l, infos = [], [], [], []
             for c in range(Cn):
+                cnt = new_tile_counts(W, H, dev) if N > 0 else None
                 project(means, quats, scales, opacities, sh, sh_degree, viewmats[c], Ks[c], camposs[c], W, H, eps2d, near,
-                        far, radius_clip, out=(radii[c], splats[c], tpg[c]))
+                        far, radius_clip, out=(radii[c], splats[c], tpg[c]), tile_counts=cnt)
                 cap = None if capacities is None else int(capacities[c] if hasattr(capacities, "__len__") else capacities)
-                keys, vals, offsets, info = intersect(radii[c], splats[c], tpg[c], W, H, c, Cn, capacity=cap)
+                keys, vals, offsets, info = intersect(radii[c], splats[c], tpg[c], W, H, c, Cn, capacity=cap, counts=cnt)
                 blend_forward(W, H, N, splats[c], vals, offsets, out=(colors[c], alphas[c], last_ids[c]))
                 keys_l.append(keys)
                 vals_l.append(vals)

@@ -654,7 +654,7 @@ def main():
     I_loc = float(np.mean(n_isect_local))
     # algorithmic bytes: per view 568N + 112I + 68P; dominant kernel = blend_bwd: 44I + 44P per launch
     step_bytes = N_VIEWS * (568 * N_GAUSS + 68 * P) + 112 * float(np.sum(n_isect_all))
-    per_launch_bytes = {"project_fwd": 284 * N_GAUSS, "tile_count_scan": 16 * N_GAUSS, "tile_scatter_sort": 16 * N_GAUSS + 28 * I_loc,
+    per_launch_bytes = {"project_fwd": 284 * N_GAUSS, "project_fwd_counts": 284 * N_GAUSS, "tile_count_scan": 16 * N_GAUSS, "tile_scatter_sort": 16 * N_GAUSS + 28 * I_loc,
                         "blend_fwd": 44 * I_loc + 24 * P, "blend_bwd": 44 * I_loc + 44 * P,
                         "project_bwd_multi": N_GAUSS * (40 + 44 + Cl * 104), "sh_bwd_multi": N_GAUSS * (204 + 204 + N_VIEWS * 12)}
     dom = max((k for k in stage_ms if k in per_launch_bytes), key=lambda k: stage_ms[k] * stage_calls.get(k, 1))

@@ -47,6 +47,13 @@ int adb_raster_project_fwd(int N, const float* means, const float* quats, const 
                            const float* viewmat, const float* K, const float* campos, int W, int H, float eps2d,
                            float near_plane, float far_plane, float radius_clip, int32_t* radii /*[N,2]*/,
                            float* splats /*[N,12]*/, int32_t* tiles_per_gauss /*[N]*/, adb_stream_t stream);
+/* adb_raster_project_fwd + the first stage of the tile-bucketed intersection fused in (one RED per (Gaussian, touched tile) into
+ * tile_counts, see adb_raster_tile_count_scan); follow it with adb_raster_tile_scan instead of adb_raster_tile_count_scan. */
+int adb_raster_project_fwd_counts(int N, const float* means, const float* quats, const float* scales,
+                                  const float* opacities, const float* sh, int sh_degree, const float* viewmat,
+                                  const float* K, const float* campos, int W, int H, float eps2d, float near_plane,
+                                  float far_plane, float radius_clip, int32_t* radii, float* splats,
+                                  int32_t* tiles_per_gauss, int32_t* tile_counts, adb_stream_t stream);
 int adb_raster_scan_workspace_bytes(int N, size_t* bytes /*HOST*/);
 int adb_raster_isect_scan(int N, const int32_t* tiles_per_gauss, int64_t* cum_tiles /*[N] inclusive*/, void* ws,
                           size_t ws_bytes, adb_stream_t stream);
@@ -86,6 +93,8 @@ int adb_raster_sh_bwd_multi(int N, int C, const float* means, const float* sh, i
 int adb_raster_tile_count_scan(int N, const int32_t* radii, const float* splats, const int32_t* tiles_per_gauss, int W, int H,
                                int legacy, long long capacity, int32_t* tile_counts, int32_t* tile_offsets, long long* total,
                                int32_t* overflow, adb_stream_t stream);
+int adb_raster_tile_scan(int W, int H, long long capacity, int32_t* tile_counts, int32_t* tile_offsets, long long* total,
+                         int32_t* overflow, adb_stream_t stream);
 int adb_raster_tile_scatter_sort(int N, const int32_t* radii, const float* splats, const int32_t* tiles_per_gauss, int W, int H,
                                  int legacy, int cam_id, int n_cams, long long capacity, int32_t* tile_counts,
                                  const int32_t* tile_offsets, void* packed, int64_t* keys, int32_t* vals, adb_stream_t stream);

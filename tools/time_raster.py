@@ -27,9 +27,10 @@ info = {}
 
 
 def step():
+    cnt = R.new_tile_counts(W, H, dev) if os.environ.get("ADB_FUSED_COUNT", "1") == "1" else None
     radii, splats, tpg = R.project(t["means"], t["quats"], t["scales"], t["opacities"], t["sh"], 3, Vd, Kd, campos, W, H,
-                                   0.01, 0.01, 1e10, 0.0)
-    keys, vals, offs, n = R.intersect(radii, splats, tpg, W, H)
+                                   0.01, 0.01, 1e10, 0.0, tile_counts=cnt)
+    keys, vals, offs, n = R.intersect(radii, splats, tpg, W, H, counts=cnt)
     colors, alphas, last = R.blend_forward(W, H, N, splats, vals, offs)
     v_splats = R.blend_backward(W, H, N, splats, vals, offs, alphas, last, vcd, vad)
     _lib.call("adb_raster_project_bwd", N, _lib.ptr(t["means"]), _lib.ptr(t["quats"]), _lib.ptr(t["scales"]),
