@@ -7,7 +7,7 @@
 // SimplicialLLT, the step is copied back, a retraction kernel updates the poses and `delta_norm.item()` syncs again.
 //
 // Here the whole solve stays on the device and no iteration touches the host:
-//   gn_edge_kernel      one CTA per edge.  The reference's two Jacobian halves satisfy Ji = -Jj exactly (it computes Jj by the
+//   gn_edge_kernel      several CTAs per edge (the points are split so that the GPU is full).  The reference's two Jacobian halves satisfy Ji = -Jj exactly (it computes Jj by the
 //                       adjoint and negates it), so the 14x14 block is [[S,-S],[-S,S]] with ONE symmetric 7x7 S: 28 + 7
 //                       accumulators per thread instead of 105 + 14, reduced with warp shuffles (35 values) instead of 119
 //                       block-wide shared-memory trees.
@@ -104,6 +104,7 @@ gn_edge_kernel(GnParams p, int n_pts, const float* __restrict__ poses, const flo
                float* __restrict__ v_out) {
     if (*done) return;
     const int e = blockIdx.x, tid = threadIdx.x;
+    const int n_split = gridDim.y, part = blockIdx.y;       // an edge's points are split over gridDim.y CTAs
     const int ix = (int)ii[e], jx = (int)jj[e];
     __shared__ float ti[3], tj[3], tij[3], qi[4], qj[4], qij[4], sc[3];
     __shared__ float sRed[GN_THREADS / 32][35];
@@ -123,7 +124,9 @@ gn_edge_kernel(GnParams p, int n_pts, const float* __restrict__ poses, const flo
 
     const float* Xi_base = Xs + (size_t)ix * n_pts * 3;
     const float* Xj_base = Xs + (size_t)jx * n_pts * 3;
-    for (int k = tid; k < n_pts; k += GN_THREADS) {
+    const int chunk = (n_pts + n_split - 1) / n_split;
+    const int k_end = min(n_pts, (part + 1) * chunk);
+    for (int k = part * chunk + tid; k < k_end; k += GN_THREADS) {
         const bool vm = valid_match[(size_t)e * n_pts + k] != 0;
         const long long ind = vm ? idx[(size_t)e * n_pts + k] : 0;
         const float Xi[3] = {Xi_base[ind * 3], Xi_base[ind * 3 + 1], Xi_base[ind * 3 + 2]};
@@ -206,8 +209,9 @@ gn_edge_kernel(GnParams p, int n_pts, const float* __restrict__ poses, const flo
         float r = 0.f;
 #pragma unroll
         for (int w_ = 0; w_ < GN_THREADS / 32; ++w_) r += sRed[w_][tid];
-        if (tid < 28) S_out[(size_t)e * 28 + tid] = r;
-        else v_out[(size_t)e * 7 + tid - 28] = r;
+        // S_out / v_out are zeroed per iteration; the CTAs of one edge add their partial sums
+        if (tid < 28) atomicAdd(S_out + (size_t)e * 28 + tid, r);
+        else atomicAdd(v_out + (size_t)e * 7 + tid - 28, r);
     }
 }
 
@@ -434,8 +438,16 @@ ADB_API int adb_gauss_newton(int mode, int n_poses, int n_pts, int n_edges, floa
     int* it_p = state_out, *done_p = state_out + 1, *ok_p = state_out + 3;
     float* delta_p = (float*)(state_out + 2);
     p.Kdev = K4;
+    // enough CTAs to fill the GPU: the reference launches one 256-thread CTA per edge (128 edges = 128 CTAs on 148 SMs);
+    // here every edge's points are split so that about 8 CTAs per SM are in flight
+    int n_split = (148 * 8 + n_edges - 1) / n_edges;
+    const int max_split = (n_pts + 4 * GN_THREADS - 1) / (4 * GN_THREADS);
+    if (n_split > max_split) n_split = max_split;
+    if (n_split < 1) n_split = 1;
     for (int it = 0; it < max_iter; ++it) {
-        gn_edge_kernel<<<n_edges, GN_THREADS, 0, stream>>>(p, n_pts, poses, Xs, Cs, ii, jj, idx_ii2jj, valid_match, Q, done_p, S, v);
+        ADB_CUDA(cudaMemsetAsync(S, 0, (size_t)n_edges * 35 * 4, stream));     // S and v are contiguous
+        gn_edge_kernel<<<dim3(n_edges, n_split), GN_THREADS, 0, stream>>>(p, n_pts, poses, Xs, Cs, ii, jj, idx_ii2jj,
+                                                                        valid_match, Q, done_p, S, v);
         ADB_CHECK_LAUNCH("gn_edge_kernel");
         ADB_CUDA(cudaMemsetAsync(H, 0, ((size_t)D * D + D) * 8, stream));
         gn_assemble_kernel<<<n_edges, 64, 0, stream>>>(n_edges, D, num_fix, ii, jj, S, v, done_p, H, b);

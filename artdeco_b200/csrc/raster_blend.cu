@@ -144,12 +144,14 @@ __device__ __forceinline__ void write_dummy(float4* __restrict__ rec) {
 //     the same bound the per-pixel pre-test uses, so a culled splat would have failed that pre-test on every pixel of the
 //     block and the image is unchanged.  ~1.5 warp-instructions per (warp, splat) because 32 splats are tested per
 //     instruction, against ~35 (forward) / ~55 (backward) for the evaluation it avoids.
-__device__ __forceinline__ bool splat_hits(const float4& A, const float4& B, const WarpRect& r) {
+__device__ __forceinline__ bool splat_box_hits(const float4& A, const float4& B, const WarpRect& r) {
     const unsigned pr = __float_as_uint(B.w);
     // 65535 is the saturation value written by the projection: treat it as unbounded
     const float rx = (pr & 0xffffu) == 0xffffu ? 3.0e38f : (float)(pr & 0xffffu);
     const float ry = (pr >> 16) == 0xffffu ? 3.0e38f : (float)(pr >> 16);
-    if (!((A.x + rx >= r.xlo) && (A.x - rx <= r.xhi) && (A.y + ry >= r.ylo) && (A.y - ry <= r.yhi))) return false;
+    return (A.x + rx >= r.xlo) && (A.x - rx <= r.xhi) && (A.y + ry >= r.ylo) && (A.y - ry <= r.yhi);
+}
+__device__ __forceinline__ bool splat_exact_hits(const float4& A, const float4& B, const WarpRect& r) {
     const float x0 = r.xlo - A.x, x1 = r.xhi - A.x, y0 = r.ylo - A.y, y1 = r.yhi - A.y;
     if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;   // centre inside the block
     const float ha = A.z, b = A.w, hc = B.x;
@@ -174,17 +176,35 @@ __device__ __forceinline__ bool splat_hits(const float4& A, const float4& B, con
 
 // Builds the warp's hit list for the staged batch (ascending slot order), padded to a multiple of 4 with DUMMY.
 // `limit`: only slots s with s >= limit are considered (the backward skips splats behind the warp's last contributor).
+// Two dense phases: (1) the cheap integer-radius box test on all slots, survivors compacted into the list; (2) the exact
+// ellipse-vs-rectangle test on the survivors only (46 % of the slots at the bench workload), 32 per instruction, compacted in
+// place (the write index never passes the read index).  A single fused test would run the expensive half with most lanes idle.
 __device__ __forceinline__ int build_hit_list(const float4* __restrict__ sRec, unsigned short* __restrict__ list,
                                               int bsize, int limit, const WarpRect& rect, int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
-    int nhit = 0;
+    int nbox = 0;
     for (int c0 = (limit > 0 ? (limit & ~31) : 0); c0 < bsize; c0 += 32) {
         const int s = c0 + lane;
         bool hit = false;
-        if (s < bsize && s >= limit) hit = splat_hits(sRec[s * 3], sRec[s * 3 + 1], rect);
+        if (s < bsize && s >= limit) hit = splat_box_hits(sRec[s * 3], sRec[s * 3 + 1], rect);
         const unsigned mask = __ballot_sync(FULL, hit);
+        if (hit) list[nbox + __popc(mask & lt_mask)] = (unsigned short)s;
+        nbox += __popc(mask);
+    }
+    __syncwarp();
+    int nhit = 0;
+    for (int c0 = 0; c0 < nbox; c0 += 32) {
+        const int k = c0 + lane;
+        int s = 0;
+        bool hit = false;
+        if (k < nbox) {
+            s = list[k];
+            hit = splat_exact_hits(sRec[s * 3], sRec[s * 3 + 1], rect);
+        }
+        const unsigned mask = __ballot_sync(FULL, hit);     // every lane has read its entry before any lane overwrites one
         if (hit) list[nhit + __popc(mask & lt_mask)] = (unsigned short)s;
         nhit += __popc(mask);
+        __syncwarp();
     }
     if (lane < 3) list[nhit + lane] = (unsigned short)DUMMY;
     __syncwarp();

@@ -204,20 +204,21 @@ tile_count_kernel(int N, const int32_t* __restrict__ radii, const float* __restr
 
 // Single CTA, 1024 threads, over the T*COPIES counters in (tile-major, copy-minor) order.
 // starts[e] = min(capacity, sum_{f<e} counts[f]);  offsets[t] = starts[t*COPIES];  offsets[T] = min(capacity, total).
-// Each thread owns 32 consecutive counters (8 tiles x 4 copies): all eight 128-bit loads are in flight at once, one
-// block-wide scan of the per-thread sums per 32768 counters (1080p: a single round; the first version looped 8 times with
+// Each thread owns 16 consecutive counters (4 tiles x 4 copies): four 128-bit loads in flight, one block-wide scan of the
+// per-thread sums per 16384 counters (1080p: two rounds; the first version looped 8 times with
 // four barriers each and took 20 us).
-__global__ void __launch_bounds__(1024)
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int T, const int32_t* __restrict__ counts, long long capacity, int32_t* __restrict__ starts,
                  int32_t* __restrict__ offsets, long long* __restrict__ total, int32_t* __restrict__ overflow) {
-    constexpr int PER = 32;
+    constexpr int PER = 16;                                  // 1024 threads x 16 counters = 16384 per round, no spills
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = T * COPIES;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < E; base += 1024 * PER) {
+    for (int base = 0; base < E; base += SCAN_THREADS * PER) {
         const int e0 = base + tid * PER;
         int c[PER];
 #pragma unroll
@@ -239,7 +240,7 @@ tile_scan_kernel(int T, const int32_t* __restrict__ counts, long long capacity, 
         if (lane == 31) s_warp[warp] = x;
         __syncthreads();
         if (warp == 0) {
-            long long w = s_warp[lane];
+            long long w = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const long long y = __shfl_up_sync(0xffffffffu, w, o);
@@ -264,7 +265,7 @@ tile_scan_kernel(int T, const int32_t* __restrict__ counts, long long capacity, 
             }
         }
         __syncthreads();
-        if (tid == 1023) s_carry = carry + s_warp[31];
+        if (tid == SCAN_THREADS - 1) s_carry = carry + s_warp[SCAN_THREADS / 32 - 1];
         __syncthreads();
     }
     if (tid == 0) {
@@ -495,7 +496,7 @@ static int tile_bucket_impl(int convention, int N, const int32_t* radii, const f
                                                                tile_counts);
         ADB_CHECK_LAUNCH("tile_count_kernel");
     }
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(T, tile_counts, capacity, tile_counts + (size_t)T * COPIES, tile_offsets, total,
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(T, tile_counts, capacity, tile_counts + (size_t)T * COPIES, tile_offsets, total,
                                             overflow);
     ADB_CHECK_LAUNCH("tile_scan_kernel");
     return ADB_OK;

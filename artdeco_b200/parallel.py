@@ -58,6 +58,7 @@ class MultiViewExchange:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.split_sh = False       # see raster.multi_view_backward: local-first SH expansion, measured slower, opt-in
         self.views_local = views_local
         self.geom = torch.zeros(n_gaussians * GEOM_FLOATS, dtype=torch.float32, device=device)
         self.views = {}

@@ -391,7 +391,11 @@ def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, campo
         return v_means, v_quats, v_scales, v_opac, v_sh, v_views, v_campos
     exchange.start_reduce()                       # geometry bucket (v_means | v_quats | v_scales | v_opac live in it)
     v_means_sh = exchange.scratch_means
-    split = getattr(exchange, "world", 1) > 1 and getattr(exchange, "rank", None) is not None and out.get("g_rgb") is not None
+    # Split expansion (local views first, the gathered ones after): measured SLOWER on 2xB200 (5.78 vs 5.65 ms per step) — the
+    # second pass re-reads and re-writes v_sh and re-evaluates its loop, which costs more than the gather latency it hides —
+    # so it is opt-in (exchange.split_sh = True).
+    split = (getattr(exchange, "split_sh", False) and getattr(exchange, "world", 1) > 1
+             and getattr(exchange, "rank", None) is not None and out.get("g_rgb") is not None)
     if split:
         # the LOCAL views' colour gradients are expanded while the other ranks' are still being gathered ...
         g_loc = out["g_rgb"]
