@@ -9,8 +9,9 @@ B200 specifics:
   * the whole local compute (projection -> tile-bucketed intersection -> blend fwd -> blend bwd, per view) has no host
     sync (intersection buffers are sized by a capacity measured once) and is captured in ONE CUDA graph;
   * gradients are produced by the multi-view backward kernels (parameters read once, gradients written once);
-  * multi-GPU: ``parallel.MultiViewExchange`` — 12 B colour gradients all-gathered, 11 geometry floats all-reduced, both
-    overlapped with the two backward kernels, instead of a dense [N,59] all-reduce.
+  * multi-GPU: 12 B colour gradients all-gathered, 11 geometry floats all-reduced, both overlapped with the two backward
+    kernels, instead of a dense [N,59] all-reduce — by ``peer.PeerExchange`` (this library's kernels storing into the other
+    GPUs' memory over NVLink) or, where peer mapping is unavailable, ``parallel.MultiViewExchange`` (NCCL).
 """
 from __future__ import annotations
 
@@ -18,7 +19,7 @@ import torch
 
 from . import _lib
 from . import raster as R
-from .parallel import MultiViewExchange
+from .peer import make_exchange
 
 KEYS = ("means", "quats", "scales", "opacities", "sh")
 
@@ -26,9 +27,11 @@ KEYS = ("means", "quats", "scales", "opacities", "sh")
 class MultiViewStep:
     def __init__(self, params: dict, viewmats: torch.Tensor, Ks: torch.Tensor, W: int, H: int, world: int = 1,
                  sh_degree: int = 3, eps2d: float = 0.01, near: float = 0.01, far: float = 1e10, radius_clip: float = 0.0,
-                 graph: bool = True, capacity_margin: float = 1.25, overlap_views: bool = False):
+                 graph: bool = True, capacity_margin: float = 1.25, overlap_views: bool = False,
+                 exchange_kind: str | None = None):
         """``params``: dict of the five parameter tensors on the device; ``viewmats [C,4,4]``, ``Ks [C,3,3]``: the LOCAL
-        views (``parallel.views_for_rank``).  ``world`` > 1 needs an initialised process group."""
+        views (``parallel.views_for_rank``).  ``world`` > 1 needs an initialised process group; ``exchange_kind``: "peer"
+        (default; falls back to NCCL where peer mapping is unavailable) or "nccl" (``ADB_EXCHANGE`` overrides the default)."""
         _lib.require_cuda(params["means"])
         self.p = {k: params[k].detach().contiguous() for k in KEYS}
         self.dev = self.p["means"].device
@@ -47,7 +50,8 @@ class MultiViewStep:
         self.v_colors = torch.zeros(C, H, W, 4, dtype=torch.float32, device=dev)     # static upstream-gradient buffers
         self.v_alphas = torch.zeros(C, H, W, dtype=torch.float32, device=dev)
         self.world = world
-        self.exchange = MultiViewExchange(N, C, dev) if world > 1 else None
+        self.exchange = make_exchange(N, C, dev, kind=exchange_kind) if world > 1 else None     # peer-memory kernels, else NCCL collectives
+        self._fused_push = getattr(self.exchange, "fused_mask", False)
         self.grads = {"v_sh": torch.empty(N, 16, 3, dtype=torch.float32, device=dev)}
         if self.exchange is not None:
             self.grads.update(self.exchange.views)          # geometry gradients live in the all-reduce bucket
@@ -83,9 +87,17 @@ class MultiViewStep:
         col, alp, last = R.blend_forward(W, H, N, self.splats[c], vals, offs)
         R.blend_backward(W, H, N, self.splats[c], vals, offs, alp, last, self.v_colors[c], self.v_alphas[c],
                          out=self.v_splats[c])
-        if self.exchange is not None:
+        if self.exchange is not None and not self._fused_push:
             R.mask_rgb_grad(self.splats[c], self.v_splats[c], self.grads["g_rgb"][c])
         return col, alp, info, (keys, vals, offs, last)
+
+    def _gather_view(self, c):
+        """Hands local view c's colour gradient to the exchange as soon as its blend backward has been issued."""
+        campos = self.P if c == 0 else None
+        if self._fused_push:
+            self.exchange.push_view(c, self.splats[c], self.v_splats[c], campos)       # mask fused with the broadcast
+        else:
+            self.exchange.start_gather_view(c, self.grads["g_rgb"][c], campos)
 
     def _local_views(self, capacity):
         """Every local view; no host sync when capacity is given."""
@@ -174,14 +186,14 @@ class MultiViewStep:
                 else:
                     for c, g in enumerate(self.graph):
                         g.replay()
-                        self.exchange.start_gather_view(c, self.grads["g_rgb"][c], self.P if c == 0 else None)
+                        self._gather_view(c)
                     self._backward()                    # 2 kernels + the all-reduce, eager (NCCL outside the graphs)
             else:
                 cols, alps, infos = [], [], []
                 for c in range(self.C):
                     col, alp, info, _ = self._view(c, self.capacity)
                     if self.exchange is not None:
-                        self.exchange.start_gather_view(c, self.grads["g_rgb"][c], self.P if c == 0 else None)
+                        self._gather_view(c)
                     cols.append(col)
                     alps.append(alp)
                     infos.append(info)

@@ -382,9 +382,17 @@ def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, campo
         mask_rgb_grad(splats, v_splats, g_rgb)
         if exchange is not None:
             exchange.start_gather(g_rgb, Pc)
+    # an exchange with separate input / result buffers (peer.PeerExchange): the kernel writes this rank's partial sums into
+    # `views_in`, the reduced gradients appear in `views`
+    gin = getattr(exchange, "views_in", None) if exchange is not None else None
+    pm, pq, ps, po = (gin["v_means"], gin["v_quats"], gin["v_scales"], gin["v_opac"]) if gin is not None else \
+        (v_means, v_quats, v_scales, v_opac)
     _lib.call("adb_raster_project_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(quats), _lib.ptr(scales), _lib.ptr(Vc),
-              _lib.ptr(Kc), W, H, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(v_splats), _lib.ptr(v_means),
-              _lib.ptr(v_quats), _lib.ptr(v_scales), _lib.ptr(v_opac), None, _lib.ptr(v_views), _lib.stream())
+              _lib.ptr(Kc), W, H, _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(v_splats), _lib.ptr(pm),
+              _lib.ptr(pq), _lib.ptr(ps), _lib.ptr(po), None, _lib.ptr(v_views), _lib.stream())
+    if gin is not None:
+        gout = exchange.views
+        v_means, v_quats, v_scales, v_opac = gout["v_means"], gout["v_quats"], gout["v_scales"], gout["v_opac"]
     if exchange is None:
         _lib.call("adb_raster_sh_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(sh), int(sh_degree), _lib.ptr(Pc),
                   _lib.ptr(g_rgb), _lib.ptr(v_sh), _lib.ptr(v_means), 1, 0, 0, _lib.ptr(v_campos), _lib.stream())

@@ -578,10 +578,16 @@ def main():
             ex.wait_reduce()
         ms_comm = timed(comm_only, 10, 3, dev, world)
         moved = (world - 1) / world * (N_VIEWS * N_GAUSS * 12) + 2 * (world - 1) / world * N_GAUSS * 44
-        collective = {"ms": ms_comm, "bytes_all_gather_total": N_VIEWS * N_GAUSS * 12, "bytes_all_reduce_payload": N_GAUSS * 44,
+        peer = type(ex).__name__ == "PeerExchange"
+        if peer:
+            ex.check()
+        collective = {"ms": ms_comm, "impl": ("own kernels over NVLink peer memory (csrc/peer_exchange.cu): masked colour rows stored into "
+                                             "every rank's table; reduce-scatter by push + owner sum + broadcast; release/acquire "
+                                             "step counters") if peer else "NCCL all_gather_into_tensor + all_reduce",
+                      "bytes_all_gather_total": N_VIEWS * N_GAUSS * 12, "bytes_all_reduce_payload": N_GAUSS * 44,
                       "bus_GBps": moved / ms_comm / 1e6,
                       "dense_all_reduce_payload_replaced": N_GAUSS * 59 * 4,
-                      "what": "all_gather_into_tensor(g_rgb [views,N,3]) + all_reduce([N,11]) issued together, timed alone; inside "
+                      "what": "gather of g_rgb [views,N,3] + sum of [N,11] over ranks issued together, timed alone; inside "
                               "the step both overlap the backward kernels"}
     n_isect_all = n_isect_local
     if world > 1:
