@@ -346,6 +346,141 @@ sh_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* 
     else                { v_means[3 * i] = gm[0];  v_means[3 * i + 1] = gm[1];  v_means[3 * i + 2] = gm[2]; }
 }
 
+
+// ---- split form of the SH backward for the multi-GPU step -------------------------------------------------------------------
+// The fused kernel above does two things per (Gaussian, view): the outer product basis(dir) (x) g into v_sh, and the gradient of
+// the colour through the view DIRECTION into v_means.  Only the first needs the other ranks' colour gradients; the second is
+// linear in the views, so each rank computes it for its LOCAL views and the geometry all-reduce sums it.  That leaves the
+// replicated part — the expansion of ALL views on every rank — without the 192 B coefficient read, the basis gradients and
+// half of the registers.
+
+// basis values only, degree <= 3
+__device__ __forceinline__ void sh_basis_values(int deg, float x, float y, float z, float* B) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) B[k] = 0.f;
+    B[0] = 0.2820947917738781f;
+    if (deg < 1) return;
+    B[1] = -0.48860251190292f * y; B[2] = 0.48860251190292f * z; B[3] = -0.48860251190292f * x;
+    if (deg < 2) return;
+    const float z2 = z * z, fT0B = -1.092548430592079f * z;
+    const float fC1 = x * x - y * y, fS1 = 2.f * x * y;
+    B[4] = 0.5462742152960395f * fS1; B[5] = fT0B * y; B[6] = 0.9461746957575601f * z2 - 0.3153915652525201f;
+    B[7] = fT0B * x; B[8] = 0.5462742152960395f * fC1;
+    if (deg < 3) return;
+    const float fT0C = -2.285228997322329f * z2 + 0.4570457994644658f, fT1B = 1.445305721320277f * z;
+    const float fC2 = x * fC1 - y * fS1, fS2 = x * fS1 + y * fC1;
+    B[9] = -0.5900435899266435f * fS2; B[10] = fT1B * fS1; B[11] = fT0C * y;
+    B[12] = z * (1.865881662950577f * z2 - 1.119528997770346f); B[13] = fT0C * x; B[14] = fT1B * fC1;
+    B[15] = -0.5900435899266435f * fC2;
+}
+
+// v_sh[i] = sum_c basis(dir_c(i)) (x) g_rgb[c][i]   (overwritten)
+__global__ void __launch_bounds__(PB)
+sh_expand_multi_kernel(int N, int C, const float* __restrict__ means, int sh_degree, const float* __restrict__ campos,
+                       const float* __restrict__ g_rgb, float* __restrict__ v_sh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float mx = means[3 * i], my = means[3 * i + 1], mz = means[3 * i + 2];
+    float o48[48];
+#pragma unroll
+    for (int k = 0; k < 48; ++k) o48[k] = 0.f;
+    const float* gp = g_rgb + (size_t)i * 3;
+    float gn0 = gp[0], gn1 = gp[1], gn2 = gp[2];
+    for (int c = 0; c < C; ++c) {
+        const float g0 = gn0, g1 = gn1, g2 = gn2;
+        if (c + 1 < C) {                                  // next view's colour gradient in flight while this one is expanded
+            const float* gq = g_rgb + ((size_t)(c + 1) * N + i) * 3;
+            gn0 = gq[0]; gn1 = gq[1]; gn2 = gq[2];
+        }
+        if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+        const float dx = mx - campos[3 * c], dy = my - campos[3 * c + 1], dz = mz - campos[3 * c + 2];
+        const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+        float Bs[16];
+        sh_basis_values(sh_degree, dx * inv, dy * inv, dz * inv, Bs);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            o48[3 * k] = fmaf(Bs[k], g0, o48[3 * k]);
+            o48[3 * k + 1] = fmaf(Bs[k], g1, o48[3 * k + 1]);
+            o48[3 * k + 2] = fmaf(Bs[k], g2, o48[3 * k + 2]);
+        }
+    }
+    float4* op = reinterpret_cast<float4*>(v_sh + (size_t)i * 48);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) op[k] = make_float4(o48[4 * k], o48[4 * k + 1], o48[4 * k + 2], o48[4 * k + 3]);
+}
+
+// v_means[i] += sum over the LOCAL views of the colour gradient pulled back through the view direction; v_campos[c] gets the
+// opposite.  The colour gradient of view c is taken from the blend backward's accumulators with the SH clamp mask applied
+// (splats[c][i].rgb > 0 ? v_splats[c][i][6:9] : 0 — raster.mask_rgb_grad).
+__global__ void __launch_bounds__(PB)
+sh_dir_bwd_multi_kernel(int N, int C, const float* __restrict__ means, const float* __restrict__ sh, int sh_degree,
+                        const float* __restrict__ campos, const float* __restrict__ splats, const float* __restrict__ v_splats,
+                        float* __restrict__ v_means, float* __restrict__ v_campos) {
+    __shared__ float sRed[PB / 32][3];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < N;
+    float mu[3] = {0.f, 0.f, 0.f};
+    float c48[48];
+#pragma unroll
+    for (int k = 0; k < 48; ++k) c48[k] = 0.f;
+    if (in) {
+        mu[0] = means[3 * i]; mu[1] = means[3 * i + 1]; mu[2] = means[3 * i + 2];
+        const float4* sp = reinterpret_cast<const float4*>(sh + (size_t)i * 48);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const float4 q = adb_ldg_stream4(sp + k);
+            c48[4 * k] = q.x; c48[4 * k + 1] = q.y; c48[4 * k + 2] = q.z; c48[4 * k + 3] = q.w;
+        }
+    }
+    float gm[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+        float red[3] = {0.f, 0.f, 0.f};
+        float g[3] = {0.f, 0.f, 0.f};
+        if (in) {
+            const size_t rec = ((size_t)c * N + i) * ADB_SPLAT_STRIDE;
+            const float4 Cc = __ldg(reinterpret_cast<const float4*>(splats + rec) + 2);
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(v_splats + rec) + 1);
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(v_splats + rec) + 2);
+            g[0] = Cc.x > 0.f ? v1.z : 0.f;
+            g[1] = Cc.y > 0.f ? v1.w : 0.f;
+            g[2] = Cc.z > 0.f ? v2.x : 0.f;
+        }
+        if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {
+            const float dx = mu[0] - campos[3 * c], dy = mu[1] - campos[3 * c + 1], dz = mu[2] - campos[3 * c + 2];
+            const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+            const float nx = dx * inv, ny = dy * inv, nz = dz * inv;
+            float Bs[16], Bx[16], By[16], Bz[16];
+            sh_basis_grad(sh_degree, nx, ny, nz, Bs, Bx, By, Bz);
+            float vnx = 0.f, vny = 0.f, vnz = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float sk = fmaf(c48[3 * k], g[0], fmaf(c48[3 * k + 1], g[1], c48[3 * k + 2] * g[2]));
+                vnx = fmaf(Bx[k], sk, vnx); vny = fmaf(By[k], sk, vny); vnz = fmaf(Bz[k], sk, vnz);
+            }
+            const float dot = vnx * nx + vny * ny + vnz * nz;
+            const float gx = (vnx - dot * nx) * inv, gy = (vny - dot * ny) * inv, gz = (vnz - dot * nz) * inv;
+            gm[0] += gx; gm[1] += gy; gm[2] += gz;
+            red[0] = -gx; red[1] = -gy; red[2] = -gz;
+        }
+        if (v_campos) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) red[k] = adb_warp_sum(red[k]);
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            __syncthreads();
+            if (lane == 0) { sRed[wid][0] = red[0]; sRed[wid][1] = red[1]; sRed[wid][2] = red[2]; }
+            __syncthreads();
+            if (threadIdx.x < 3) {
+                float v = 0.f;
+#pragma unroll
+                for (int w_ = 0; w_ < PB / 32; ++w_) v += sRed[w_][threadIdx.x];
+                if (v != 0.f) atomicAdd(v_campos + 3 * c + threadIdx.x, v);
+            }
+        }
+    }
+    if (!in) return;
+    v_means[3 * i] += gm[0]; v_means[3 * i + 1] += gm[1]; v_means[3 * i + 2] += gm[2];
+}
+
 }  // namespace
 
 // Geometry gradients of C views summed per Gaussian.  radii [C,N,2], splats / v_splats [C,N,12] (stacked per camera),
@@ -384,5 +519,30 @@ ADB_API int adb_raster_sh_bwd_multi(int N, int C, const float* means, const floa
     sh_bwd_multi_kernel<<<adb_cdiv(N, PB), PB, 0, stream>>>(N, C, means, sh, sh_degree, campos, g_rgb, v_sh, v_means,
                                                            accumulate, skip_mod, skip_val, v_campos);
     ADB_CHECK_LAUNCH("sh_bwd_multi_kernel");
+    return ADB_OK;
+}
+
+// Split form for the multi-GPU step (see the kernels): adb_raster_sh_dir_bwd_multi adds the LOCAL views' direction term to
+// v_means [N,3] (and v_campos [C,3], may be NULL) straight from the blend backward's accumulators splats / v_splats [C,N,12];
+// adb_raster_sh_expand_multi overwrites v_sh [N,48] with sum_c basis(dir_c) (x) g_rgb[c] over ALL views (g_rgb [C,N,3] and
+// campos [C,3] may hold views rendered on other GPUs).  Together they equal adb_raster_sh_bwd_multi.
+ADB_API int adb_raster_sh_dir_bwd_multi(int N, int C, const float* means, const float* sh, int sh_degree, const float* campos,
+                                        const float* splats, const float* v_splats, float* v_means, float* v_campos,
+                                        cudaStream_t stream) {
+    ADB_REQUIRE(N >= 0 && C >= 1 && sh_degree >= 0 && sh_degree <= 3, "adb_raster_sh_dir_bwd_multi: bad sizes");
+    if (N == 0) return ADB_OK;
+    ADB_REQUIRE(means && sh && campos && splats && v_splats && v_means, "adb_raster_sh_dir_bwd_multi: null pointer");
+    sh_dir_bwd_multi_kernel<<<adb_cdiv(N, PB), PB, 0, stream>>>(N, C, means, sh, sh_degree, campos, splats, v_splats, v_means,
+                                                               v_campos);
+    ADB_CHECK_LAUNCH("sh_dir_bwd_multi_kernel");
+    return ADB_OK;
+}
+ADB_API int adb_raster_sh_expand_multi(int N, int C, const float* means, int sh_degree, const float* campos, const float* g_rgb,
+                                       float* v_sh, cudaStream_t stream) {
+    ADB_REQUIRE(N >= 0 && C >= 1 && sh_degree >= 0 && sh_degree <= 3, "adb_raster_sh_expand_multi: bad sizes");
+    if (N == 0) return ADB_OK;
+    ADB_REQUIRE(means && campos && g_rgb && v_sh, "adb_raster_sh_expand_multi: null pointer");
+    sh_expand_multi_kernel<<<adb_cdiv(N, PB), PB, 0, stream>>>(N, C, means, sh_degree, campos, g_rgb, v_sh);
+    ADB_CHECK_LAUNCH("sh_expand_multi_kernel");
     return ADB_OK;
 }

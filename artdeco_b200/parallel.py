@@ -47,18 +47,19 @@ class MultiViewExchange:
     gradients, and the SH gradient of one view is the outer product basis(dir_view)[16] x v_rgb[3]: it is fully determined by
     12 bytes per (view, Gaussian) plus the view's camera centre.  So the ranks
       * ALL-GATHER the clamp-masked colour gradients ``g_rgb [C_local, N, 3]`` (12 MB per view) and the camera centres, and
-        every rank expands the SH gradient of ALL views locally (``adb_raster_sh_bwd_multi``);
-      * ALL-REDUCE only the 11 geometry floats per Gaussian (44 MB) — one flat bucket the backward kernel writes into.
-    Both collectives are asynchronous: the gather overlaps the geometry kernel, the reduce overlaps the SH kernel
+        every rank expands the SH gradient of ALL views locally (``adb_raster_sh_expand_multi``);
+      * ALL-REDUCE only the 11 geometry floats per Gaussian (44 MB) — one flat bucket the backward kernels write into (the
+        colour's gradient through the view direction is added per rank for its local views, ``adb_raster_sh_dir_bwd_multi``).
+    Both collectives are asynchronous: the gather overlaps the geometry kernels, the reduce overlaps the expansion
     (``raster.multi_view_backward``).  Result on every rank: exactly the sum over all views of the single-view gradients.
-    Works with NCCL (GPU) and gloo (CPU tests)."""
+    Works with NCCL (GPU) and gloo (CPU tests).  On CUDA the default is ``peer.PeerExchange`` — the same exchange by this
+    library's own kernels over NVLink peer memory; this class is the library-collective fallback."""
 
     def __init__(self, n_gaussians: int, views_local: int, device, group=None):
         self.n = n_gaussians
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.split_sh = False       # see raster.multi_view_backward: local-first SH expansion, measured slower, opt-in
         self.views_local = views_local
         self.geom = torch.zeros(n_gaussians * GEOM_FLOATS, dtype=torch.float32, device=device)
         self.views = {}
@@ -71,7 +72,6 @@ class MultiViewExchange:
         # so that a view's gather can start as soon as ITS blend backward has finished, while the next view is still rendering)
         self.g_all = torch.empty(views_local, self.world, n_gaussians, 3, dtype=torch.float32, device=device)
         self.campos_all = torch.empty(views_local, self.world, 3, dtype=torch.float32, device=device)
-        self.scratch_means = torch.empty(n_gaussians, 3, dtype=torch.float32, device=device)
         self._gather, self._reduce = [], None
         self._views_started = 0
         self.bytes_per_step = {"all_gather_recv": (self.world - 1) * views_local * n_gaussians * 12,

@@ -89,7 +89,6 @@ class PeerExchange:
         self.rank = rank if rank is not None else dist.get_rank(group)
         if not 1 <= self.world <= MAXW or views_local > N_SLOTS - SLOT_G:
             raise _lib.ArtdecoB200Error(f"PeerExchange supports at most {MAXW} ranks")
-        self.split_sh = False
         self.timeout_s = timeout_s
         L = self.layout = PeerRegion(n_gaussians, views_local, self.world)
         with torch.cuda.device(self.dev):
@@ -125,7 +124,6 @@ class PeerExchange:
                 v = buf[o:o + n_gaussians * m]
                 d[name] = v.view(n_gaussians, m) if m > 1 else v
             o += n_gaussians * m
-        self.scratch_means = torch.empty(n_gaussians, 3, dtype=torch.float32, device=self.dev)
         self.step_g = self.step_r = 0
         self._views_started = 0
         self._campos = None

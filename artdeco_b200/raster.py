@@ -37,6 +37,8 @@ _lib.register("adb_raster_project_bwd", [i32, vp, vp, vp, vp, i32, vp, vp, vp, i
 
 _lib.register("adb_raster_project_bwd_multi", [i32, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 _lib.register("adb_raster_sh_bwd_multi", [i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp])
+_lib.register("adb_raster_sh_dir_bwd_multi", [i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp])
+_lib.register("adb_raster_sh_expand_multi", [i32, i32, vp, i32, vp, vp, vp, vp])
 
 _lib.register("adb_raster_project_fwd_legacy", [i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32,
                                                 vp, vp, vp, vp])
@@ -356,9 +358,9 @@ def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, campo
 
     ``out``: optional dict of preallocated gradient tensors (``v_means [N,3], v_quats [N,4], v_scales [N,3], v_opac [N],
     v_sh [N,16,3]``), e.g. views of a flat communication bucket.
-    ``exchange`` (multi-GPU; ``parallel.MultiViewExchange``): the colour gradients of the local views are all-gathered while
-    the geometry kernel runs, the 11 geometry floats are all-reduced while the SH kernel expands the colour gradients of
-    EVERY rank's views; ``None`` = single process.  Returns (v_means, v_quats, v_scales, v_opac, v_sh, v_viewmats[C,4,4],
+    ``exchange`` (multi-GPU; ``peer.PeerExchange`` or ``parallel.MultiViewExchange``): the colour gradients of the local views
+    are gathered while the geometry kernels run, the 11 geometry floats are summed over ranks while the SH gradient of EVERY
+    rank's views is expanded; ``None`` = single process.  Returns (v_means, v_quats, v_scales, v_opac, v_sh, v_viewmats[C,4,4],
     v_campos[C,3] of the local views)."""
     N, Cn = means.shape[0], viewmats.shape[0]
     dev = means.device
@@ -397,25 +399,17 @@ def multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, campo
         _lib.call("adb_raster_sh_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(sh), int(sh_degree), _lib.ptr(Pc),
                   _lib.ptr(g_rgb), _lib.ptr(v_sh), _lib.ptr(v_means), 1, 0, 0, _lib.ptr(v_campos), _lib.stream())
         return v_means, v_quats, v_scales, v_opac, v_sh, v_views, v_campos
-    exchange.start_reduce()                       # geometry bucket (v_means | v_quats | v_scales | v_opac live in it)
-    v_means_sh = exchange.scratch_means
-    # Split expansion (local views first, the gathered ones after): measured SLOWER on 2xB200 (5.78 vs 5.65 ms per step) — the
-    # second pass re-reads and re-writes v_sh and re-evaluates its loop, which costs more than the gather latency it hides —
-    # so it is opt-in (exchange.split_sh = True).
-    split = (getattr(exchange, "split_sh", False) and getattr(exchange, "world", 1) > 1
-             and getattr(exchange, "rank", None) is not None and out.get("g_rgb") is not None)
-    if split:
-        # the LOCAL views' colour gradients are expanded while the other ranks' are still being gathered ...
-        g_loc = out["g_rgb"]
-        _lib.call("adb_raster_sh_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(sh), int(sh_degree), _lib.ptr(Pc), _lib.ptr(g_loc),
-                  _lib.ptr(v_sh), _lib.ptr(v_means_sh), 0, 0, 0, None, _lib.stream())
+    # Multi-GPU: the SH backward in its split form.  The direction term (gradient of the colour w.r.t. the mean through the view
+    # direction) is linear in the views, so each rank adds it for its LOCAL views to its partial geometry sums and the reduce
+    # carries it; only the outer product basis(dir) (x) v_rgb needs every rank's colour gradients, and that expansion — the
+    # part every rank repeats for all views — then runs without the SH coefficients and the basis gradients.
+    _lib.call("adb_raster_sh_dir_bwd_multi", N, Cn, _lib.ptr(means), _lib.ptr(sh), int(sh_degree), _lib.ptr(Pc), _lib.ptr(splats),
+              _lib.ptr(v_splats), _lib.ptr(pm), _lib.ptr(v_campos), _lib.stream())
+    exchange.start_reduce()                       # geometry sums (v_means | v_quats | v_scales | v_opac), overlaps the expansion
     g_all, P_all = exchange.wait_gather()
-    # ... then every other rank's views are added (view-major table: entry c belongs to rank c % world)
-    _lib.call("adb_raster_sh_bwd_multi", N, int(g_all.shape[0]), _lib.ptr(means), _lib.ptr(sh), int(sh_degree),
-              _lib.ptr(P_all), _lib.ptr(g_all), _lib.ptr(v_sh), _lib.ptr(v_means_sh), 3 if split else 0,
-              exchange.world if split else 0, exchange.rank if split else 0, None, _lib.stream())
+    _lib.call("adb_raster_sh_expand_multi", N, int(g_all.shape[0]), _lib.ptr(means), int(sh_degree), _lib.ptr(P_all),
+              _lib.ptr(g_all), _lib.ptr(v_sh), _lib.stream())
     exchange.wait_reduce()
-    v_means.add_(v_means_sh)
     return v_means, v_quats, v_scales, v_opac, v_sh, v_views, v_campos
 
 

@@ -662,7 +662,8 @@ def main():
     step_bytes = N_VIEWS * (568 * N_GAUSS + 68 * P) + 112 * float(np.sum(n_isect_all))
     per_launch_bytes = {"project_fwd": 284 * N_GAUSS, "project_fwd_counts": 284 * N_GAUSS, "tile_count_scan": 16 * N_GAUSS, "tile_scatter_sort": 16 * N_GAUSS + 28 * I_loc,
                         "blend_fwd": 44 * I_loc + 24 * P, "blend_bwd": 44 * I_loc + 44 * P,
-                        "project_bwd_multi": N_GAUSS * (40 + 44 + Cl * 104), "sh_bwd_multi": N_GAUSS * (204 + 204 + N_VIEWS * 12)}
+                        "project_bwd_multi": N_GAUSS * (40 + 44 + Cl * 104), "sh_bwd_multi": N_GAUSS * (204 + 204 + N_VIEWS * 12),
+                        "sh_dir_bwd_multi": N_GAUSS * (204 + 24 + Cl * 48), "sh_expand_multi": N_GAUSS * (12 + 192 + N_VIEWS * 12)}
     dom = max((k for k in stage_ms if k in per_launch_bytes), key=lambda k: stage_ms[k] * stage_calls.get(k, 1))
     dom_gbs = per_launch_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
     # secondary bound: FP32 issue.  No-cull model: 256 pixel-threads x I splats x (25 FLOP + 1 MUFU)

@@ -80,6 +80,15 @@ int adb_raster_sh_bwd_multi(int N, int C, const float* means, const float* sh, i
                             const float* g_rgb, float* v_sh, float* v_means, int accumulate /* bit0: v_means +=, bit1: v_sh += */,
                             int skip_mod, int skip_val /* skip views c % skip_mod == skip_val when skip_mod > 0 */,
                             float* v_campos, adb_stream_t stream);
+/* Split form of adb_raster_sh_bwd_multi for the multi-GPU step: adb_raster_sh_dir_bwd_multi ADDS the direction term of the C
+ * LOCAL views to v_means [N,3] (v_campos [C,3] accumulated, may be NULL), taking each view's colour gradient from the blend
+ * backward's accumulators with the SH clamp mask (splats[c][i].rgb > 0 ? v_splats[c][i][6:9] : 0; splats / v_splats [C,N,12]) —
+ * linear in the views, so the geometry all-reduce sums it over ranks; adb_raster_sh_expand_multi OVERWRITES v_sh [N,48] with
+ * sum_c basis(dir_c) (x) g_rgb[c] over all C views of the batch (g_rgb [C,N,3], campos [C,3]: any rank's views). */
+int adb_raster_sh_dir_bwd_multi(int N, int C, const float* means, const float* sh, int sh_degree, const float* campos,
+                                const float* splats, const float* v_splats, float* v_means, float* v_campos, adb_stream_t stream);
+int adb_raster_sh_expand_multi(int N, int C, const float* means, int sh_degree, const float* campos, const float* g_rgb,
+                               float* v_sh, adb_stream_t stream);
 /* Tile-bucketed intersection (no library sort, no host sync; bit-identical to adb_raster_isect_emit + adb_raster_sort +
  * adb_raster_tile_offsets, i.e. to gsplat's isect_tiles / radix sort / isect_offset_encode behind h3dgsv3.py:664-680):
  *   adb_raster_tile_count_scan   per-tile counts (RED.ADD) + one-CTA exclusive scan -> tile_offsets[T+1] clamped to

@@ -130,9 +130,14 @@ def test_multi_view_backward_through_peer_exchange_matches_single_process(cuda):
     world = 2
     exs, bases = _virtual_ranks(N, 2, world, cuda)
     # Both "ranks" are driven by ONE host thread here: rank 0's wait kernels spin until this thread has enqueued rank 1's work, so
-    # nothing launched in between may be a first launch (lazy module loading waits for the device to drain).  The single-process
-    # call above has loaded the library's kernels; this loads the in-place add the backward ends with.
-    torch.zeros(N, 3, device=cuda).add_(torch.ones(N, 3, device=cuda))
+    # nothing launched in between may be a first launch (lazy module loading waits for the device to drain).  Load the two
+    # kernels of the split SH backward now (the single-process call above used the fused one).
+    from artdeco_b200 import _lib
+    z = torch.zeros(4, 48, device=cuda)
+    _lib.call("adb_raster_sh_dir_bwd_multi", 4, 1, _lib.ptr(z), _lib.ptr(z), 3, _lib.ptr(z), _lib.ptr(z), _lib.ptr(z),
+              _lib.ptr(torch.zeros(4, 3, device=cuda)), None, _lib.stream())
+    _lib.call("adb_raster_sh_expand_multi", 4, 1, _lib.ptr(z), 3, _lib.ptr(z), _lib.ptr(z), _lib.ptr(torch.zeros(4, 48, device=cuda)),
+              _lib.stream())
     torch.cuda.synchronize()
     views = [[0, 2], [1, 3]]                               # parallel.views_for_rank
     loc = [local(v) for v in views]

@@ -183,9 +183,9 @@ def test_multi_view_batch_equals_sum_of_single_views(cuda):
 
 @pytest.mark.gpu
 def test_multi_view_exchange_algebra_matches_single_process(cuda):
-    """The multi-GPU exchange of parallel.MultiViewExchange (all-gather of 12 B colour gradients + all-reduce of the 11
-    geometry floats, SH gradient of every view expanded locally) emulated in one process: 4 views split over two "ranks"
-    must reproduce the single-process 4-view gradients."""
+    """The multi-GPU exchange (gather of 12 B colour gradients + sum of the 11 geometry floats, SH gradient of every view expanded
+    locally, direction term added per rank) emulated in one process: 4 views split over two "ranks" must reproduce the
+    single-process 4-view gradients."""
     from artdeco_b200 import raster as R
     N, W, H = 20000, 480, 272
     sc = synthetic.raster_scene(N, seed=8)
@@ -215,10 +215,9 @@ def test_multi_view_exchange_algebra_matches_single_process(cuda):
     ra, sa, va_ = local(idx_all)
     full = R.multi_view_backward(t["means"], t["quats"], t["scales"], t["sh"], 3, Vs, Ks, P, W, H, ra, sa, va_)
 
-    class FakeExchange:            # what NCCL does, done by hand: "rank" 0 = views 0,1; "rank" 1 = views 2,3
-        def __init__(self):
-            self.scratch_means = torch.empty(N, 3, device=cuda)
-            self.g, self.p = [], []
+    class FakeExchange:            # what the exchange does, done by hand: "rank" 0 = views 0,1; "rank" 1 = views 2,3
+        def __init__(self, g_all=None, p_all=None):
+            self.g, self.p, self.g_all, self.p_all = [], [], g_all, p_all
 
         def start_gather(self, g_rgb, campos):
             self.g.append(g_rgb.clone()); self.p.append(campos.clone())
@@ -227,33 +226,39 @@ def test_multi_view_exchange_algebra_matches_single_process(cuda):
             pass
 
         def wait_gather(self):
-            return torch.cat(self.g_all), torch.cat(self.p_all)
+            return self.g_all, self.p_all
 
         def wait_reduce(self):
             pass
 
-    # pass 1: each rank's local geometry gradients and colour gradients
-    parts = []
+    # pass 1: what each rank hands to the gather (its local views' masked colour gradients and camera centres)
+    loc, rows = [], []
     for ranks_views in ([0, 1], [2, 3]):
         r_, s_, v_ = local(ranks_views)
-        ex = FakeExchange()
-        ex.g_all, ex.p_all = [torch.zeros(2, N, 3, device=cuda)] * 2, [P[ranks_views]] * 2     # placeholder gather
+        loc.append((r_, s_, v_))
+        rows.append(R.mask_rgb_grad(s_, v_, torch.empty(2, N, 3, device=cuda)))
+    g_all, p_all = torch.cat(rows), torch.cat([P[[0, 1]], P[[2, 3]]])
+    # pass 2: every rank's backward with the gathered table; its geometry outputs are PARTIAL sums (local views only, the
+    # colour's direction term included) that the reduce adds up
+    parts = []
+    for k_, ranks_views in enumerate(([0, 1], [2, 3])):
+        r_, s_, v_ = loc[k_]
+        ex = FakeExchange(g_all, p_all)
         out = R.multi_view_backward(t["means"], t["quats"], t["scales"], t["sh"], 3, Vs[ranks_views], Ks[ranks_views],
                                     P[ranks_views], W, H, r_, s_, v_, exchange=ex)
-        parts.append((ex.g[0], ex.p[0], [o.clone() for o in out[:4]], ex.scratch_means.clone()))
-    # zero colour gradients in the placeholder gather => out[0] = geometry-only v_means (+ 0): sum them like the all-reduce
-    geo = [sum(p[2][k] for p in parts) for k in range(4)]
-    g_all, p_all = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
-    v_sh = torch.empty(N, 16, 3, device=cuda)
-    v_means_sh = torch.empty(N, 3, device=cuda)
+        assert torch.equal(ex.g[0], rows[k_]), "the backward hands the masked colour gradients of its local views to the gather"
+        parts.append([o.clone() for o in out[:5]])
+    for k_, name in enumerate(("v_means", "v_quats", "v_scales", "v_opac")):
+        assert rel_err(parts[0][k_] + parts[1][k_], full[k_]) < 2e-5, name
+    assert rel_err(parts[0][4], full[4]) < 2e-5 and torch.equal(parts[0][4], parts[1][4]), "v_sh expanded from the gathered rows"
+    v_sh, v_means_sh = torch.empty(N, 16, 3, device=cuda), torch.empty(N, 3, device=cuda)
     from artdeco_b200 import _lib
     _lib.call("adb_raster_sh_bwd_multi", N, 4, _lib.ptr(t["means"]), _lib.ptr(t["sh"]), 3, _lib.ptr(p_all), _lib.ptr(g_all),
               _lib.ptr(v_sh), _lib.ptr(v_means_sh), 0, 0, 0, None, _lib.stream())
-    assert rel_err(geo[0] + v_means_sh, full[0]) < 2e-5, "v_means"
-    assert rel_err(geo[1], full[1]) < 2e-5 and rel_err(geo[2], full[2]) < 2e-5 and rel_err(geo[3], full[3]) < 2e-5
-    assert rel_err(v_sh, full[4]) < 2e-5, "v_sh expanded from gathered colour gradients"
-    # split expansion used on multi-GPU runs: "rank 0" expands its local views (0,1) first, then adds the others from the
-    # view-major gathered table [C_local, world] (entry c belongs to rank c % world) with its own entries skipped
+    assert rel_err(v_sh, full[4]) < 2e-5, "fused kernel on the gathered table"
+    parts = [(rows[0], P[[0, 1]].contiguous()), (rows[1], P[[2, 3]].contiguous())]
+    # accumulate / skip options of the fused kernel: "rank 0" expands its local views (0,1) first, then adds the others from
+    # a view-major gathered table [C_local, world] (entry c belongs to rank c % world) with its own entries skipped
     world, rank = 2, 0
     g_vm = torch.stack([torch.stack([parts[r][0][c] for r in range(world)]) for c in range(2)]).reshape(4, N, 3).contiguous()
     p_vm = torch.stack([torch.stack([parts[r][1][c] for r in range(world)]) for c in range(2)]).reshape(4, 3).contiguous()
