@@ -20,6 +20,7 @@
 // (nobody can scatter step e+1 before every rank has signalled the end of its step-e reduction).
 #include "common.cuh"
 #include "raster_common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -66,40 +67,41 @@ __global__ void peer_wait_kernel(const unsigned* __restrict__ flags, int world, 
 __global__ void __launch_bounds__(256)
 peer_push_rgb_kernel(int N, const float* __restrict__ splats, const float* __restrict__ v_splats, PeerPtrs dst, int world,
                      size_t row_off, const float* __restrict__ campos, PeerPtrs cam, size_t cam_off) {
-    // 4 Gaussians per thread: 12 floats = three 128-bit stores per destination
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    // 4 Gaussians per thread and iteration: 12 floats = three 128-bit stores per destination
     if (blockIdx.x == 0 && threadIdx.x < 3 && campos) {
         const float v = campos[threadIdx.x];
         for (int r = 0; r < world; ++r) reinterpret_cast<float*>(cam.p[r])[cam_off + threadIdx.x] = v;
     }
-    const int i0 = q * 4;
-    if (i0 >= N) return;
-    float g[12];
+    const int nq = (N + 3) / 4;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const int i0 = q * 4;
+        float g[12];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k;
-        if (i < N) {
-            const float4 C = __ldg(reinterpret_cast<const float4*>(splats + (size_t)i * ADB_SPLAT_STRIDE) + 2);
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(v_splats + (size_t)i * ADB_SPLAT_STRIDE) + 1);
-            const float4 v2 = __ldg(reinterpret_cast<const float4*>(v_splats + (size_t)i * ADB_SPLAT_STRIDE) + 2);
-            g[3 * k] = C.x > 0.f ? v1.z : 0.f;
-            g[3 * k + 1] = C.y > 0.f ? v1.w : 0.f;
-            g[3 * k + 2] = C.z > 0.f ? v2.x : 0.f;
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k;
+            if (i < N) {
+                const float4 C = __ldg(reinterpret_cast<const float4*>(splats + (size_t)i * ADB_SPLAT_STRIDE) + 2);
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(v_splats + (size_t)i * ADB_SPLAT_STRIDE) + 1);
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(v_splats + (size_t)i * ADB_SPLAT_STRIDE) + 2);
+                g[3 * k] = C.x > 0.f ? v1.z : 0.f;
+                g[3 * k + 1] = C.y > 0.f ? v1.w : 0.f;
+                g[3 * k + 2] = C.z > 0.f ? v2.x : 0.f;
+            } else {
+                g[3 * k] = g[3 * k + 1] = g[3 * k + 2] = 0.f;
+            }
+        }
+        if (i0 + 4 <= N) {
+            for (int r = 0; r < world; ++r) {
+                float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst.p[r]) + row_off + (size_t)i0 * 3);
+                d[0] = make_float4(g[0], g[1], g[2], g[3]);
+                d[1] = make_float4(g[4], g[5], g[6], g[7]);
+                d[2] = make_float4(g[8], g[9], g[10], g[11]);
+            }
         } else {
-            g[3 * k] = g[3 * k + 1] = g[3 * k + 2] = 0.f;
-        }
-    }
-    if (i0 + 4 <= N) {
-        for (int r = 0; r < world; ++r) {
-            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst.p[r]) + row_off + (size_t)i0 * 3);
-            d[0] = make_float4(g[0], g[1], g[2], g[3]);
-            d[1] = make_float4(g[4], g[5], g[6], g[7]);
-            d[2] = make_float4(g[8], g[9], g[10], g[11]);
-        }
-    } else {
-        for (int r = 0; r < world; ++r) {
-            float* d = reinterpret_cast<float*>(dst.p[r]) + row_off + (size_t)i0 * 3;
-            for (int k = 0; k < (N - i0) * 3; ++k) d[k] = g[k];
+            for (int r = 0; r < world; ++r) {
+                float* d = reinterpret_cast<float*>(dst.p[r]) + row_off + (size_t)i0 * 3;
+                for (int k = 0; k < (N - i0) * 3; ++k) d[k] = g[k];
+            }
         }
     }
 }
@@ -154,9 +156,22 @@ int fill_ptrs(PeerPtrs* pp, void* const* ptrs, int world) {
     return ADB_OK;
 }
 
+// CTAs per exchange kernel.  The kernels are NVLink-bound, not SM-bound: a few dozen CTAs saturate the links, while a grid over
+// every SM fills all load/store units with remote stores and stalls whatever runs beside it (measured on 8 GPUs: the geometry
+// backward next to an all-SM push took 0.31 ms instead of 0.08).  ADB_PEER_CTAS overrides (1..2368).
+int peer_ctas() {
+    static int n = [] {
+        const char* e = getenv("ADB_PEER_CTAS");
+        const int v = e ? atoi(e) : 32;
+        return v < 1 ? 1 : (v > 148 * 16 ? 148 * 16 : v);
+    }();
+    return n;
+}
+
 int grid_for(size_t n, int threads) {
     const size_t g = (n + threads - 1) / threads;
-    return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+    const size_t cap = (size_t)peer_ctas();
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
 }  // namespace
@@ -237,7 +252,7 @@ ADB_API int adb_peer_push_rgb(int N, const float* splats, const float* v_splats,
     PeerPtrs d, c = {};
     ADB_REQUIRE(fill_ptrs(&d, dst_ptrs, world) == ADB_OK, "adb_peer_push_rgb: null peer pointer");
     if (campos) ADB_REQUIRE(cam_ptrs && fill_ptrs(&c, cam_ptrs, world) == ADB_OK, "adb_peer_push_rgb: null camera pointer");
-    peer_push_rgb_kernel<<<adb_cdiv(adb_cdiv(N, 4), 256), 256, 0, stream>>>(N, splats, v_splats, d, world, row_off, campos, c, cam_off);
+    peer_push_rgb_kernel<<<grid_for((size_t)adb_cdiv(N, 4), 256), 256, 0, stream>>>(N, splats, v_splats, d, world, row_off, campos, c, cam_off);
     ADB_CHECK_LAUNCH("peer_push_rgb_kernel");
     return ADB_OK;
 }

@@ -9,9 +9,9 @@ B200 specifics:
   * the whole local compute (projection -> tile-bucketed intersection -> blend fwd -> blend bwd, per view) has no host
     sync (intersection buffers are sized by a capacity measured once) and is captured in ONE CUDA graph;
   * gradients are produced by the multi-view backward kernels (parameters read once, gradients written once);
-  * multi-GPU: 12 B colour gradients all-gathered, 11 geometry floats all-reduced, both overlapped with the two backward
-    kernels, instead of a dense [N,59] all-reduce — by ``peer.PeerExchange`` (this library's kernels storing into the other
-    GPUs' memory over NVLink) or, where peer mapping is unavailable, ``parallel.MultiViewExchange`` (NCCL).
+  * multi-GPU: 12 B colour gradients all-gathered, 11 geometry floats all-reduced, both overlapped with the backward
+    kernels, instead of a dense [N,59] all-reduce — by ``parallel.MultiViewExchange`` (NCCL, default) or ``peer.PeerExchange``
+    (this library's kernels storing into the other GPUs' memory over NVLink; ``exchange_kind="peer"`` / ``ADB_EXCHANGE=peer``).
 """
 from __future__ import annotations
 
@@ -30,8 +30,9 @@ class MultiViewStep:
                  graph: bool = True, capacity_margin: float = 1.25, overlap_views: bool = False,
                  exchange_kind: str | None = None):
         """``params``: dict of the five parameter tensors on the device; ``viewmats [C,4,4]``, ``Ks [C,3,3]``: the LOCAL
-        views (``parallel.views_for_rank``).  ``world`` > 1 needs an initialised process group; ``exchange_kind``: "peer"
-        (default; falls back to NCCL where peer mapping is unavailable) or "nccl" (``ADB_EXCHANGE`` overrides the default)."""
+        views (``parallel.views_for_rank``).  ``world`` > 1 needs an initialised process group; ``exchange_kind``: "nccl"
+        (library collectives, the default) or "peer" (this library's kernels over NVLink peer memory); ``ADB_EXCHANGE`` sets
+        the default (``peer.make_exchange``)."""
         _lib.require_cuda(params["means"])
         self.p = {k: params[k].detach().contiguous() for k in KEYS}
         self.dev = self.p["means"].device
@@ -50,7 +51,7 @@ class MultiViewStep:
         self.v_colors = torch.zeros(C, H, W, 4, dtype=torch.float32, device=dev)     # static upstream-gradient buffers
         self.v_alphas = torch.zeros(C, H, W, dtype=torch.float32, device=dev)
         self.world = world
-        self.exchange = make_exchange(N, C, dev, kind=exchange_kind) if world > 1 else None     # peer-memory kernels, else NCCL collectives
+        self.exchange = make_exchange(N, C, dev, kind=exchange_kind) if world > 1 else None
         self._fused_push = getattr(self.exchange, "fused_mask", False)
         self.grads = {"v_sh": torch.empty(N, 16, 3, dtype=torch.float32, device=dev)}
         if self.exchange is not None:

@@ -52,8 +52,8 @@ class MultiViewExchange:
         colour's gradient through the view direction is added per rank for its local views, ``adb_raster_sh_dir_bwd_multi``).
     Both collectives are asynchronous: the gather overlaps the geometry kernels, the reduce overlaps the expansion
     (``raster.multi_view_backward``).  Result on every rank: exactly the sum over all views of the single-view gradients.
-    Works with NCCL (GPU) and gloo (CPU tests).  On CUDA the default is ``peer.PeerExchange`` — the same exchange by this
-    library's own kernels over NVLink peer memory; this class is the library-collective fallback."""
+    Works with NCCL (GPU) and gloo (CPU tests).  ``peer.PeerExchange`` is the same exchange by this library's own kernels over
+    NVLink peer memory (opt-in, see ``peer.make_exchange``)."""
 
     def __init__(self, n_gaussians: int, views_local: int, device, group=None):
         self.n = n_gaussians

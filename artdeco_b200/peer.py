@@ -281,13 +281,22 @@ class PeerExchange:
 
 
 def make_exchange(n_gaussians: int, views_local: int, device, group=None, kind: str | None = None):
-    """The multi-GPU gradient exchange for ``multiview.MultiViewStep`` / ``rasterization(grad_exchange=)``: peer-memory kernels
-    on CUDA when every rank can map every other rank's region (``ADB_EXCHANGE=nccl`` forces the library collectives), else
-    ``parallel.MultiViewExchange``."""
+    """The multi-GPU gradient exchange for ``multiview.MultiViewStep`` / ``rasterization(grad_exchange=)``.
+
+    ``kind`` (default: ``$ADB_EXCHANGE``, else "nccl"):
+      * "nccl" — ``parallel.MultiViewExchange``, the library collectives;
+      * "peer" — ``PeerExchange``, this library's kernels over NVLink peer memory (falls back to "nccl", with a warning, when the
+        ranks cannot map each other's memory).
+    Measured on B200s (profiles/r02_summary.md): the peer exchange alone is faster than the two NCCL collectives (0.25 vs 0.31 ms
+    on 2 GPUs, 0.34 vs 0.39 ms on 8) and equal inside the 2-GPU step, but its first version — grids over every SM — slowed the
+    backward kernels running beside it on 8 GPUs (step 1.99 vs 1.71 ms); the grids are capped since (``ADB_PEER_CTAS``), which
+    has not been re-measured on 8 GPUs, so the library collectives stay the default."""
     import os
 
     from .parallel import MultiViewExchange
-    kind = kind or os.environ.get("ADB_EXCHANGE", "peer")
+    kind = kind or os.environ.get("ADB_EXCHANGE", "nccl")
+    if kind not in ("nccl", "peer"):
+        raise ValueError(f"exchange kind must be 'nccl' or 'peer', got {kind!r}")
     dev = torch.device(device)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if kind == "peer" and dev.type == "cuda" and 1 < world <= MAXW and n_gaussians % 4 == 0:
