@@ -156,13 +156,15 @@ int fill_ptrs(PeerPtrs* pp, void* const* ptrs, int world) {
     return ADB_OK;
 }
 
-// CTAs per exchange kernel.  The kernels are NVLink-bound, not SM-bound: a few dozen CTAs saturate the links, while a grid over
-// every SM fills all load/store units with remote stores and stalls whatever runs beside it (measured on 8 GPUs: the geometry
-// backward next to an all-SM push took 0.31 ms instead of 0.08).  ADB_PEER_CTAS overrides (1..2368).
+// CTAs per exchange kernel (ADB_PEER_CTAS, 1..2368; default: no cap below 16 CTAs per SM).  The kernels are NVLink-bound, and
+// the trade-off is measured but not yet tuned: with grids over every SM the exchange alone takes 0.25 ms on 2 GPUs and 0.34 ms
+// on 8, but on 8 GPUs the remote stores of all 148 SMs stall the backward kernels running beside the push (project_bwd_multi
+// 0.31 ms instead of 0.08); with 32 CTAs of 256 threads that contention cannot occur, but the copies lose memory parallelism
+// (0.59 ms alone on 2 GPUs).
 int peer_ctas() {
     static int n = [] {
         const char* e = getenv("ADB_PEER_CTAS");
-        const int v = e ? atoi(e) : 32;
+        const int v = e ? atoi(e) : 148 * 16;
         return v < 1 ? 1 : (v > 148 * 16 ? 148 * 16 : v);
     }();
     return n;
