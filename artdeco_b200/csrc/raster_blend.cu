@@ -211,6 +211,27 @@ __device__ __forceinline__ int build_hit_list(const float4* __restrict__ sRec, u
     return nhit;
 }
 
+// The backward's hit list from the forward's per-entry warp masks (bit w of hit_mask[sorted index] = warp w's block is hit):
+// the forward has already run both tests on every entry a warp can need again — the backward only revisits entries up to the
+// warp's last contributor, all of which lie in batches that warp went through — so the backward replaces ~150 instructions
+// per 32 slots by a table look-up and a compaction.  sM[slot] = mask of the staged batch (slot order = back to front).
+__device__ __forceinline__ int build_hit_list_from_mask(const unsigned char* __restrict__ sM, unsigned short* __restrict__ list,
+                                                        int bsize, int limit, int warp, int lane) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int nhit = 0;
+    for (int c0 = (limit > 0 ? (limit & ~31) : 0); c0 < bsize; c0 += 32) {
+        const int s = c0 + lane;
+        const bool hit = s < bsize && s >= limit && ((sM[s] >> warp) & 1u);
+        const unsigned mask = __ballot_sync(FULL, hit);
+        if (hit) list[nhit + __popc(mask & lt_mask)] = (unsigned short)s;
+        nhit += __popc(mask);
+    }
+    __syncwarp();
+    if (lane < 3) list[nhit + lane] = (unsigned short)DUMMY;
+    __syncwarp();
+    return nhit;
+}
+
 // LEGACY = Inria conventions (ADB_CONV_INRIA): alpha <= 0.99, stop when T(1-alpha) < 1e-4 (strict), 4th channel
 // accumulates 1/z, and main_ids gets the Gaussian with the largest blending weight alpha*T per pixel (-1: none).
 template <bool LEGACY, bool ASYNC>
@@ -218,12 +239,13 @@ __global__ void __launch_bounds__(BLOCK, 4)
 blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* __restrict__ vals,
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
                  float* __restrict__ colors, float* __restrict__ alphas, int32_t* __restrict__ last_ids,
-                 int32_t* __restrict__ main_ids) {
+                 int32_t* __restrict__ main_ids, unsigned char* __restrict__ hit_mask) {
     constexpr float MAXA = LEGACY ? ADB_MAX_ALPHA_INRIA : ADB_MAX_ALPHA;
     constexpr int NBUF = ASYNC ? 2 : 1;
     __shared__ __align__(16) float4 sRecBuf[NBUF][(BLOCK + 1) * 3];
     __shared__ __align__(8) unsigned short sList[NWARP][LIST_STRIDE];
     __shared__ __align__(8) uint64_t sBar[2];
+    __shared__ unsigned sMask[BLOCK / 4];       // byte s = warp mask of slot s of the current batch (hit_mask != NULL)
 
     const int tw = (W + ADB_TILE - 1) / ADB_TILE;
     const int tile = blockIdx.y * tw + blockIdx.x;
@@ -234,6 +256,20 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const WarpRect rect{(float)x0 + 0.5f, (float)x0 + 7.5f, (float)y0 + 0.5f, (float)y0 + 3.5f};
     const int start = tile_offsets[tile], end = tile_offsets[tile + 1];
+    if (tid < BLOCK / 4) sMask[tid] = 0u;
+    // Writes the finished batch's warp masks to hit_mask[start + pb*BLOCK ...] and clears the table (one thread per word, so the
+    // clear cannot race with the read; the barrier that follows orders it before the next batch's atomics).
+    auto flush_mask = [&](int pb) {
+        if (tid < BLOCK / 4) {
+            const unsigned w = sMask[tid];
+            sMask[tid] = 0u;
+            const int i0 = start + pb * BLOCK + tid * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k < end) hit_mask[i0 + k] = (unsigned char)((w >> (8 * k)) & 0xffu);
+        }
+    };
+    int pending = -1;                            // batch whose masks are complete but not written yet (block-uniform)
     if (tid == 0) {
         write_dummy(sRecBuf[0] + DUMMY * 3);
         if (ASYNC) {
@@ -260,6 +296,7 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     bool done = !inside;
     for (int b = 0; b < nb; ++b) {
         const int n_done = __syncthreads_count(done);    // also: every warp has finished reading the previous batch
+        if (hit_mask && pending >= 0) { flush_mask(pending); pending = -1; }
         const int bstart = start + b * BLOCK;
         const int idx = bstart + tid;
         float4* sRec = sRecBuf[ASYNC ? (b & 1) : 0];
@@ -278,10 +315,17 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
             if (idx < end) stage_record<LEGACY>(sRec + tid * 3, splats, vals[idx] % n_per_cam);
         }
         __syncthreads();
+        pending = b;
         const int bsize = min(BLOCK, end - bstart);
         if (__all_sync(FULL, done)) continue;
         unsigned short* list = sList[warp];
         const int nhit = build_hit_list(sRec, list, bsize, 0, rect, lane);
+        if (hit_mask) {
+            for (int k = lane; k < nhit; k += 32) {
+                const unsigned sl = list[k];
+                atomicOr(&sMask[sl >> 2], 1u << (((sl & 3u) << 3) + warp));
+            }
+        }
         int cur_t = -1;
         const int nq = (nhit + 3) >> 2;
         for (int q = 0; q < nq; ++q) {
@@ -312,6 +356,10 @@ blend_fwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
         }
         if (cur_t >= 0) cur = bstart + cur_t;
     }
+    if (hit_mask && pending >= 0) {              // the loop ran to its end: the last batch's masks are still in shared memory
+        __syncthreads();
+        flush_mask(pending);
+    }
     if (inside) {
         const size_t pix = (size_t)i * W + j;
         reinterpret_cast<float4*>(colors)[pix] = acc;
@@ -338,7 +386,8 @@ struct BwdSmem {
     static constexpr int OFF_REC = 0;                     // float4 [NBUF][(BLOCK+1)*3]
     static constexpr int OFF_G = OFF_REC + NBUF * REC_BYTES;                  // int [NBUF][BLOCK + 4]
     static constexpr int OFF_BAR = OFF_G + NBUF * G_BYTES;                    // uint64 [2]
-    static constexpr int OFF_LIST = OFF_BAR + 16;                             // u16 [NWARP][LIST_STRIDE]
+    static constexpr int OFF_M = OFF_BAR + 16;                                // u8 [BLOCK]: the forward's warp masks of the batch
+    static constexpr int OFF_LIST = OFF_M + BLOCK;                            // u16 [NWARP][LIST_STRIDE]
     static constexpr int OFF_VO = OFF_LIST + NWARP * LIST_STRIDE * 2;         // float4 [NWARP][32]
     static constexpr int OFF_V = OFF_VO + NWARP * 32 * 16;                    // float4 [NWARP][S*ROW4]
     static constexpr int BYTES = OFF_V + NWARP * S * ROW4 * 16;
@@ -351,7 +400,7 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
                  const int32_t* __restrict__ tile_offsets, int n_per_cam,
                  const float* __restrict__ alphas, const int32_t* __restrict__ last_ids,
                  const float* __restrict__ v_colors, const float* __restrict__ v_alphas,
-                 float* __restrict__ v_splats) {
+                 float* __restrict__ v_splats, const unsigned char* __restrict__ hit_mask) {
     constexpr float MAXA = LEGACY ? ADB_MAX_ALPHA_INRIA : ADB_MAX_ALPHA;
     using L = BwdSmem<S, ASYNC>;
     constexpr int HALVES = 32 / S;          // lanes per slot in the reduction phase
@@ -361,6 +410,7 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
     float4* sRec = reinterpret_cast<float4*>(smem + L::OFF_REC);
     int* sG = reinterpret_cast<int*>(smem + L::OFF_G);
     uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    unsigned char* sM = smem + L::OFF_M;
 
     const int tw = (W + ADB_TILE - 1) / ADB_TILE;
     const int tile = blockIdx.y * tw + blockIdx.x;
@@ -441,11 +491,13 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
             sG[tid] = g;
             stage_record<LEGACY>(sRec + tid * 3, splats, g);
         }
+        if (hit_mask && idx >= start) sM[tid] = hit_mask[idx];
         __syncthreads();
         // a splat at slot s contributes to this warp only if batch_end - s <= warp_bin_final
         const int limit = max(0, batch_end - warp_bin_final);
         if (limit >= bsize) continue;
-        const int nhit = build_hit_list(sRec, list, bsize, limit, rect, lane);
+        const int nhit = hit_mask ? build_hit_list_from_mask(sM, list, bsize, limit, warp, lane)
+                                  : build_hit_list(sRec, list, bsize, limit, rect, lane);
         const int tmin = inside ? batch_end - bin_final : (1 << 30);   // lane-valid iff t >= tmin
         for (int g0 = 0; g0 < nhit; g0 += S) {
             const int ng = min(S, nhit - g0);
@@ -541,7 +593,7 @@ blend_bwd_kernel(int W, int H, const float* __restrict__ splats, const int32_t* 
 
 static int blend_fwd_impl(bool legacy, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
                           const int32_t* tile_offsets, float* colors, float* alphas, int32_t* last_ids,
-                          int32_t* main_ids, cudaStream_t stream) {
+                          int32_t* main_ids, unsigned char* hit_mask, cudaStream_t stream) {
     ADB_REQUIRE(W > 0 && H > 0 && n_per_cam >= 0, "adb_raster_blend_fwd: bad sizes");
     ADB_REQUIRE(tile_offsets && colors && alphas && last_ids, "adb_raster_blend_fwd: null pointer");
     dim3 grid(adb_cdiv(W, ADB_TILE), adb_cdiv(H, ADB_TILE));
@@ -552,13 +604,13 @@ static int blend_fwd_impl(bool legacy, int W, int H, int n_per_cam, const float*
     static const int tma = getenv("ADB_BLEND_TMA") ? atoi(getenv("ADB_BLEND_TMA")) : 0;
     if (legacy)
         blend_fwd_kernel<true, false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
-                                                                 colors, alphas, last_ids, main_ids);
+                                                                 colors, alphas, last_ids, main_ids, hit_mask);
     else if (tma)
         blend_fwd_kernel<false, true><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
-                                                                 colors, alphas, last_ids, nullptr);
+                                                                 colors, alphas, last_ids, nullptr, hit_mask);
     else
         blend_fwd_kernel<false, false><<<grid, BLOCK, 0, stream>>>(W, H, splats, vals_sorted, tile_offsets, max(n_per_cam, 1),
-                                                                  colors, alphas, last_ids, nullptr);
+                                                                  colors, alphas, last_ids, nullptr, hit_mask);
     ADB_CHECK_LAUNCH("blend_fwd_kernel");
     return ADB_OK;
 }
@@ -568,7 +620,18 @@ ADB_API int adb_raster_blend_fwd(int W, int H, int n_per_cam, const float* splat
                                  const int32_t* tile_offsets, float* colors, float* alphas, int32_t* last_ids,
                                  cudaStream_t stream) {
     return blend_fwd_impl(false, W, H, n_per_cam, splats, vals_sorted, tile_offsets, colors, alphas, last_ids, nullptr,
-                          stream);
+                          nullptr, stream);
+}
+
+// Same, and hit_mask[k] (one byte per sorted intersection, k as in vals_sorted) receives the warps of entry k's tile whose 8x4
+// pixel block the splat can reach — the culling decisions of this pass, which adb_raster_blend_bwd_hits reuses.  Entries behind
+// the point where a whole tile saturated are left unwritten (the backward never looks at them).
+ADB_API int adb_raster_blend_fwd_hits(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                                      const int32_t* tile_offsets, float* colors, float* alphas, int32_t* last_ids,
+                                      unsigned char* hit_mask, cudaStream_t stream) {
+    ADB_REQUIRE(hit_mask, "adb_raster_blend_fwd_hits: null hit_mask");
+    return blend_fwd_impl(false, W, H, n_per_cam, splats, vals_sorted, tile_offsets, colors, alphas, last_ids, nullptr,
+                          hit_mask, stream);
 }
 
 // Legacy (Inria) blending: colors[...,3] = sum alpha*T/z (inverse depth); main_ids [H,W] may be NULL.
@@ -576,13 +639,13 @@ ADB_API int adb_raster_blend_fwd_legacy(int W, int H, int n_per_cam, const float
                                         const int32_t* tile_offsets, float* colors, float* alphas, int32_t* last_ids,
                                         int32_t* main_ids, cudaStream_t stream) {
     return blend_fwd_impl(true, W, H, n_per_cam, splats, vals_sorted, tile_offsets, colors, alphas, last_ids, main_ids,
-                          stream);
+                          nullptr, stream);
 }
 
 template <bool LEGACY, int S, int OCC, bool ASYNC>
 static int launch_bwd(dim3 grid, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
                       const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids, const float* v_colors,
-                      const float* v_alphas, float* v_splats, cudaStream_t stream) {
+                      const float* v_alphas, float* v_splats, const unsigned char* hit_mask, cudaStream_t stream) {
     static AdbDeviceOnce once;
     const int rc = once.ensure([]() -> int {
         ADB_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<LEGACY, S, OCC, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -591,13 +654,14 @@ static int launch_bwd(dim3 grid, int W, int H, int n_per_cam, const float* splat
     });
     if (rc != ADB_OK) return rc;
     blend_bwd_kernel<LEGACY, S, OCC, ASYNC><<<grid, BLOCK, BwdSmem<S, ASYNC>::BYTES, stream>>>(
-        W, H, splats, vals_sorted, tile_offsets, n_per_cam, alphas, last_ids, v_colors, v_alphas, v_splats);
+        W, H, splats, vals_sorted, tile_offsets, n_per_cam, alphas, last_ids, v_colors, v_alphas, v_splats, hit_mask);
     return ADB_OK;
 }
 
 static int blend_bwd_impl(bool legacy, int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
                           const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
-                          const float* v_colors, const float* v_alphas, float* v_splats, cudaStream_t stream) {
+                          const float* v_colors, const float* v_alphas, float* v_splats, const unsigned char* hit_mask,
+                          cudaStream_t stream) {
     ADB_REQUIRE(W > 0 && H > 0 && n_per_cam >= 0, "adb_raster_blend_bwd: bad sizes");
     ADB_REQUIRE(tile_offsets && alphas && last_ids && v_colors && v_alphas, "adb_raster_blend_bwd: null pointer");
     if (n_per_cam == 0) return ADB_OK;
@@ -608,7 +672,7 @@ static int blend_bwd_impl(bool legacy, int W, int H, int n_per_cam, const float*
     static const int slots = getenv("ADB_BWD_SLOTS") ? atoi(getenv("ADB_BWD_SLOTS")) : 16;
     static const int occ = getenv("ADB_BWD_OCC") ? atoi(getenv("ADB_BWD_OCC")) : 4;
     int rc;
-#define ADB_BWD_ARGS grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors, v_alphas, v_splats, stream
+#define ADB_BWD_ARGS grid, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors, v_alphas, v_splats, hit_mask, stream
     // ADB_BLEND_TMA=1: double-buffered cp.async.bulk staging (+13 KB of shared memory: 3 CTAs/SM instead of 4); measured
     // 0.667 ms vs 0.629 ms for the default, so it stays opt-in (same reason as the forward kernel).
     static const int tma = getenv("ADB_BLEND_TMA") ? atoi(getenv("ADB_BLEND_TMA")) : 0;
@@ -629,7 +693,18 @@ ADB_API int adb_raster_blend_bwd(int W, int H, int n_per_cam, const float* splat
                                  const float* v_colors, const float* v_alphas, float* v_splats,
                                  cudaStream_t stream) {
     return blend_bwd_impl(false, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
-                          v_alphas, v_splats, stream);
+                          v_alphas, v_splats, nullptr, stream);
+}
+
+// Same with the forward's culling decisions (adb_raster_blend_fwd_hits of the SAME splats / vals_sorted / tile_offsets): the
+// per-warp hit lists come from hit_mask instead of repeating the box and ellipse tests.  Identical gradients.
+ADB_API int adb_raster_blend_bwd_hits(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                                      const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
+                                      const float* v_colors, const float* v_alphas, float* v_splats,
+                                      const unsigned char* hit_mask, cudaStream_t stream) {
+    ADB_REQUIRE(hit_mask, "adb_raster_blend_bwd_hits: null hit_mask");
+    return blend_bwd_impl(false, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
+                          v_alphas, v_splats, hit_mask, stream);
 }
 
 // Legacy (Inria) conventions; v_colors[...,3] is the upstream gradient of the inverse-depth channel and v_splats slot 9
@@ -639,5 +714,5 @@ ADB_API int adb_raster_blend_bwd_legacy(int W, int H, int n_per_cam, const float
                                         const float* v_colors, const float* v_alphas, float* v_splats,
                                         cudaStream_t stream) {
     return blend_bwd_impl(true, W, H, n_per_cam, splats, vals_sorted, tile_offsets, alphas, last_ids, v_colors,
-                          v_alphas, v_splats, stream);
+                          v_alphas, v_splats, nullptr, stream);
 }

@@ -85,9 +85,10 @@ class MultiViewStep:
                   W, H, eps2d, near, far, rclip, out=(self.radii[c], self.splats[c], self.tpg[c]), tile_counts=cnt)
         cap = None if capacity is None else capacity[c]
         keys, vals, offs, info = R.intersect(self.radii[c], self.splats[c], self.tpg[c], W, H, capacity=cap, counts=cnt)
-        col, alp, last = R.blend_forward(W, H, N, self.splats[c], vals, offs)
+        hits = R.new_hit_mask(vals)                    # the forward's culling decisions, reused by the backward
+        col, alp, last = R.blend_forward(W, H, N, self.splats[c], vals, offs, hits=hits)
         R.blend_backward(W, H, N, self.splats[c], vals, offs, alp, last, self.v_colors[c], self.v_alphas[c],
-                         out=self.v_splats[c])
+                         out=self.v_splats[c], hits=hits)
         if self.exchange is not None and not self._fused_push:
             R.mask_rgb_grad(self.splats[c], self.v_splats[c], self.grads["g_rgb"][c])
         return col, alp, info, (keys, vals, offs, last)

@@ -10,6 +10,7 @@ All compute goes through the C ABI (adb_raster_*); PyTorch only owns memory, str
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -43,6 +44,8 @@ _lib.register("adb_raster_sh_expand_multi", [i32, i32, vp, i32, vp, vp, vp, vp])
 _lib.register("adb_raster_project_fwd_legacy", [i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32,
                                                 vp, vp, vp, vp])
 _lib.register("adb_raster_isect_emit_legacy", [i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp])
+_lib.register("adb_raster_blend_fwd_hits", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp])
+_lib.register("adb_raster_blend_bwd_hits", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 _lib.register("adb_raster_blend_fwd_legacy", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp])
 _lib.register("adb_raster_blend_bwd_legacy", [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 
@@ -192,9 +195,19 @@ def intersect(radii, splats, tpg, W, H, cam_id=0, n_cams=1, sort=True, legacy=Fa
     return keys[:n_isect], vals[:n_isect], offsets, n_isect
 
 
-def blend_forward(W, H, N, splats, vals, offsets, legacy=False, out=None):
+def new_hit_mask(vals: torch.Tensor):
+    """One byte per sorted intersection for ``blend_forward(hits=)`` / ``blend_backward(hits=)``: the forward records which
+    warps' pixel blocks each (tile, splat) entry can reach and the backward reuses those culling decisions instead of repeating
+    the tests.  ``ADB_BLEND_HITS=0`` returns None (both kernels then cull on their own)."""
+    if os.environ.get("ADB_BLEND_HITS", "1") == "0":
+        return None
+    return torch.empty(max(1, vals.numel()), dtype=torch.uint8, device=vals.device)
+
+
+def blend_forward(W, H, N, splats, vals, offsets, legacy=False, out=None, hits=None):
     """``legacy`` returns a 4th tensor main_ids[H,W] and accumulates 1/z in colors[...,3].
-    ``out``: optional preallocated (colors[H,W,4], alphas[H,W], last_ids[H,W]) — slices of per-camera stacks."""
+    ``out``: optional preallocated (colors[H,W,4], alphas[H,W], last_ids[H,W]) — slices of per-camera stacks.
+    ``hits``: optional uint8 [len(vals)] (``new_hit_mask``) that receives the culling decisions for ``blend_backward``."""
     dev = splats.device
     if out is not None:
         colors, alphas, last_ids = out
@@ -208,14 +221,25 @@ def blend_forward(W, H, N, splats, vals, offsets, legacy=False, out=None):
                   _lib.ptr(offsets), _lib.ptr(colors), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(main_ids),
                   _lib.stream())
         return colors, alphas, last_ids, main_ids
+    if hits is not None:
+        assert hits.dtype == torch.uint8 and hits.numel() >= vals.numel()
+        _lib.call("adb_raster_blend_fwd_hits", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
+                  _lib.ptr(offsets), _lib.ptr(colors), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(hits), _lib.stream())
+        return colors, alphas, last_ids
     _lib.call("adb_raster_blend_fwd", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
               _lib.ptr(offsets), _lib.ptr(colors), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.stream())
     return colors, alphas, last_ids
 
 
-def blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas, legacy=False, out=None):
-    """``out``: optional ZEROED [N,12] accumulator (a slice of the per-camera stack in the multi-view path)."""
+def blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas, legacy=False, out=None, hits=None):
+    """``out``: optional ZEROED [N,12] accumulator (a slice of the per-camera stack in the multi-view path).
+    ``hits``: the mask ``blend_forward(hits=)`` filled for the SAME splats / vals / offsets."""
     v_splats = out if out is not None else torch.zeros(N, SPLAT_STRIDE, dtype=torch.float32, device=splats.device)
+    if hits is not None and not legacy:
+        _lib.call("adb_raster_blend_bwd_hits", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
+                  _lib.ptr(offsets), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(v_colors), _lib.ptr(v_alphas),
+                  _lib.ptr(v_splats), _lib.ptr(hits), _lib.stream())
+        return v_splats
     _lib.call("adb_raster_blend_bwd_legacy" if legacy else "adb_raster_blend_bwd", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
               _lib.ptr(offsets), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(v_colors), _lib.ptr(v_alphas),
               _lib.ptr(v_splats), _lib.stream())
@@ -235,7 +259,9 @@ class _RasterizeOneCamera(torch.autograd.Function):
             if colors_direct is not None:
                 splats[:, 8:11] = colors_direct
             keys, vals, offsets, n_isect = intersect(radii, splats, tpg, W, H, cam_id, n_cams, counts=cnt)
-            colors, alphas, last_ids = blend_forward(W, H, N, splats, vals, offsets)
+            hits = new_hit_mask(vals)
+            colors, alphas, last_ids = blend_forward(W, H, N, splats, vals, offsets, hits=hits)
+        ctx.hits = hits
         ctx.save_for_backward(means, quats, scales, opacities, sh, viewmat, K, campos, radii, splats, vals, offsets,
                               alphas, last_ids)
         ctx.cfg = (W, H, sh_degree, eps2d, near, far, radius_clip, colors_direct is not None)
@@ -252,7 +278,7 @@ class _RasterizeOneCamera(torch.autograd.Function):
         v_colors = torch.zeros(H, W, 4, device=dev) if v_colors is None else _f32c(v_colors)
         v_alphas = torch.zeros(H, W, device=dev) if v_alphas is None else _f32c(v_alphas)
         with torch.cuda.device(dev):
-            v_splats = blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas)
+            v_splats = blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v_alphas, hits=ctx.hits)
             v_means = torch.empty_like(means)
             v_quats = torch.empty_like(quats)
             v_scales = torch.empty_like(scales)
@@ -293,14 +319,16 @@ class _RasterizeCameras(torch.autograd.Function):
             colors = torch.empty(Cn, H, W, 4, dtype=torch.float32, device=dev)
             alphas = torch.empty(Cn, H, W, dtype=torch.float32, device=dev)
             last_ids = torch.empty(Cn, H, W, dtype=torch.int32, device=dev)
-            keys_l, vals_l, offs_l, infos = [], [], [], []
+            keys_l, vals_l, offs_l, infos, hits_l = [], [], [], [], []
             for c in range(Cn):
                 cnt = new_tile_counts(W, H, dev) if N > 0 else None
                 project(means, quats, scales, opacities, sh, sh_degree, viewmats[c], Ks[c], camposs[c], W, H, eps2d, near,
                         far, radius_clip, out=(radii[c], splats[c], tpg[c]), tile_counts=cnt)
                 cap = None if capacities is None else int(capacities[c] if hasattr(capacities, "__len__") else capacities)
                 keys, vals, offsets, info = intersect(radii[c], splats[c], tpg[c], W, H, c, Cn, capacity=cap, counts=cnt)
-                blend_forward(W, H, N, splats[c], vals, offsets, out=(colors[c], alphas[c], last_ids[c]))
+                hits = new_hit_mask(vals)
+                blend_forward(W, H, N, splats[c], vals, offsets, out=(colors[c], alphas[c], last_ids[c]), hits=hits)
+                hits_l.append(hits)
                 keys_l.append(keys)
                 vals_l.append(vals)
                 offs_l.append(offsets)
@@ -308,6 +336,7 @@ class _RasterizeCameras(torch.autograd.Function):
         ctx.save_for_backward(means, quats, scales, opacities, sh, viewmats, Ks, camposs, radii, splats, alphas, last_ids,
                               *vals_l, *offs_l)
         ctx.cfg = (W, H, sh_degree, Cn)
+        ctx.hits = hits_l
         isect_ids, flatten_ids = torch.cat(keys_l), torch.cat(vals_l)
         base, offs_out = 0, []
         for c in range(Cn):                        # gsplat offsets index the concatenated list (padded in capacity mode)
@@ -335,7 +364,7 @@ class _RasterizeCameras(torch.autograd.Function):
             v_splats = torch.zeros(Cn, N, SPLAT_STRIDE, dtype=torch.float32, device=dev)
             for c in range(Cn):
                 blend_backward(W, H, N, splats[c], vals_l[c], offs_l[c], alphas[c], last_ids[c], v_colors[c], v_alphas[c],
-                               out=v_splats[c])
+                               out=v_splats[c], hits=ctx.hits[c])
             ex = ctx.exchange
             grads = multi_view_backward(means, quats, scales, sh, sh_degree, viewmats, Ks, camposs, W, H, radii, splats,
                                         v_splats, out=(dict(ex.views) if ex is not None else None), exchange=ex)

@@ -562,8 +562,10 @@ def main():
     _lib.TIMER = None
     engine.use_graph = True
     engine.overlap_views = ov
-    stage_ms = {k.replace("adb_raster_", ""): v[0] / v[1] for k, v in tot.items()}     # per LAUNCH
-    stage_calls = {k.replace("adb_raster_", ""): v[1] // k_stage for k, v in tot.items()}
+    # per LAUNCH; the *_hits entry points are the same blend kernels sharing their culling decisions (one byte per intersection)
+    short = lambda k: k.replace("adb_raster_", "").replace("_hits", "")  # noqa: E731
+    stage_ms = {short(k): v[0] / v[1] for k, v in tot.items()}
+    stage_calls = {short(k): v[1] // k_stage for k, v in tot.items()}
 
     # the exchange alone (world > 1): time and achieved bus bandwidth of the two collectives on the real buffers
     collective = None

@@ -114,6 +114,16 @@ int adb_raster_blend_bwd(int W, int H, int n_per_cam, const float* splats, const
                          const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids,
                          const float* v_colors, const float* v_alphas, float* v_splats /*[N,12] zeroed, +=*/,
                          adb_stream_t stream);
+/* The same pair sharing the culling decisions: adb_raster_blend_fwd_hits also fills hit_mask — one byte per sorted intersection
+ * (index as in vals_sorted): bit w = the splat can reach the 8x4 pixel block of warp w of its tile (entries behind the point
+ * where a whole tile saturated are left unwritten) — and adb_raster_blend_bwd_hits builds its per-warp hit lists from it
+ * instead of repeating the box and ellipse tests (same splats / vals_sorted / tile_offsets; identical gradients). */
+int adb_raster_blend_fwd_hits(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                              const int32_t* tile_offsets, float* colors, float* alphas, int32_t* last_ids,
+                              unsigned char* hit_mask, adb_stream_t stream);
+int adb_raster_blend_bwd_hits(int W, int H, int n_per_cam, const float* splats, const int32_t* vals_sorted,
+                              const int32_t* tile_offsets, const float* alphas, const int32_t* last_ids, const float* v_colors,
+                              const float* v_alphas, float* v_splats, const unsigned char* hit_mask, adb_stream_t stream);
 int adb_raster_project_bwd(int N, const float* means, const float* quats, const float* scales, const float* sh,
                            int sh_degree, const float* viewmat, const float* K, const float* campos, int W, int H,
                            float eps2d, float near_plane, float far_plane, float radius_clip, const int32_t* radii,

@@ -271,6 +271,36 @@ def test_multi_view_exchange_algebra_matches_single_process(cuda):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N,W,H,view,kw", [(3000, 320, 192, 1.0, {}), (50000, 960, 544, 5.0, dict(scale_range=(0.01, 0.15))),
+                                           (100000, 1920, 1080, 3.5, {})])
+def test_backward_from_the_forward_hit_mask_equals_backward_with_its_own_culling(cuda, N, W, H, view, kw):
+    """adb_raster_blend_fwd_hits / adb_raster_blend_bwd_hits: the forward records which warps each (tile, splat) entry can reach
+    and the backward builds its hit lists from that record.  Same images bit for bit; same gradients up to the order of the
+    floating-point REDs between tiles."""
+    from artdeco_b200 import raster as R
+    sc, V, K = _scene(N, W, H, seed=21, view=view, **kw)
+    st = _gpu_stages(sc, V, K, W, H, cuda)
+    vals, offs, splats = st["vals"], st["offs"], st["splats"]
+    hits = torch.full((max(1, vals.numel()),), 0xAB, dtype=torch.uint8, device=cuda)      # poison: unwritten entries stay unused
+    col, alp, last = R.blend_forward(W, H, N, splats, vals, offs, hits=hits)
+    assert torch.equal(col, st["colors"]) and torch.equal(alp, st["alphas"]) and torch.equal(last, st["last"])
+    vc, va = synthetic.upstream_grads(W, H, seed=2)
+    vcd, vad = vc[0].contiguous().to(cuda), va[0, ..., 0].contiguous().to(cuda)
+    g_own = R.blend_backward(W, H, N, splats, vals, offs, alp, last, vcd, vad)
+    g_hit = R.blend_backward(W, H, N, splats, vals, offs, alp, last, vcd, vad, hits=hits)
+    assert rel_err(g_hit, g_own) < 2e-6
+    # the mask is a pure function of the forward's inputs: the last contributor of every pixel must be marked for its warp
+    lastc = last.cpu().numpy()
+    hm = hits.cpu().numpy()
+    ys, xs = np.nonzero(alp.cpu().numpy() > 0)
+    sel = np.random.default_rng(0).choice(len(ys), size=min(2000, len(ys)), replace=False) if len(ys) else []
+    for k_ in sel:
+        y, x = int(ys[k_]), int(xs[k_])
+        warp = ((y % 16) // 4) * 2 + ((x % 16) // 8)
+        assert (hm[lastc[y, x]] >> warp) & 1, f"pixel ({x},{y}): its last contributor is not marked for warp {warp}"
+
+
+@pytest.mark.gpu
 def test_intersect_capacity_mode_has_no_host_sync_and_flags_overflow(cuda):
     """capacity mode of the tile-bucketed intersection: identical keys/vals/offsets without reading the count back, the true
     count and an overflow flag stay on the device, and an undersized capacity is memory-safe and flagged."""

@@ -31,8 +31,9 @@ def step():
     radii, splats, tpg = R.project(t["means"], t["quats"], t["scales"], t["opacities"], t["sh"], 3, Vd, Kd, campos, W, H,
                                    0.01, 0.01, 1e10, 0.0, tile_counts=cnt)
     keys, vals, offs, n = R.intersect(radii, splats, tpg, W, H, counts=cnt)
-    colors, alphas, last = R.blend_forward(W, H, N, splats, vals, offs)
-    v_splats = R.blend_backward(W, H, N, splats, vals, offs, alphas, last, vcd, vad)
+    hits = R.new_hit_mask(vals)                     # ADB_BLEND_HITS=0: both kernels cull on their own
+    colors, alphas, last = R.blend_forward(W, H, N, splats, vals, offs, hits=hits)
+    v_splats = R.blend_backward(W, H, N, splats, vals, offs, alphas, last, vcd, vad, hits=hits)
     _lib.call("adb_raster_project_bwd", N, _lib.ptr(t["means"]), _lib.ptr(t["quats"]), _lib.ptr(t["scales"]),
               _lib.ptr(t["sh"]), 3, _lib.ptr(Vd), _lib.ptr(Kd), _lib.ptr(campos), W, H, 0.01, 0.01, 1e10, 0.0,
               _lib.ptr(radii), _lib.ptr(splats), _lib.ptr(v_splats), _lib.ptr(gm), _lib.ptr(gq), _lib.ptr(gs),
