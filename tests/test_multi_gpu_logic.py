@@ -67,6 +67,15 @@ def _worker(rank, world, port, q):
     ok &= torch.equal(g2, g_all) and torch.equal(c2, cam_all)
     for k in exp_geo:
         ok &= bool(torch.allclose(ex.views[k], exp_geo[k], atol=1e-6))
+    # the exchange factory: on CPU tensors (gloo) both kinds resolve to the library-collective exchange; unknown kinds are refused
+    from artdeco_b200.peer import make_exchange
+    ok &= type(make_exchange(N, Cl, "cpu")).__name__ == "MultiViewExchange"
+    ok &= type(make_exchange(N, Cl, "cpu", kind="peer")).__name__ == "MultiViewExchange"
+    try:
+        make_exchange(N, Cl, "cpu", kind="mpi")
+        ok = False
+    except ValueError:
+        pass
     q.put((rank, ok))
     dist.destroy_process_group()
 
@@ -82,3 +91,36 @@ def test_gloo_world2_bucket_allreduce_and_sharding():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_peer_region_layout_is_aligned_and_disjoint():
+    """peer.PeerRegion: every block of a rank's peer-visible region starts on a 256-byte boundary, blocks do not overlap, the
+    geometry shards cover the [N,11] block and the colour rows keep the [views, N, 3] stride the expansion kernel expects."""
+    from artdeco_b200.parallel import GEOM_FLOATS
+    from artdeco_b200.peer import MAXW, N_SLOTS, PeerRegion
+    for n, cl, world in [(1_000_000, 1, 8), (1_000_000, 4, 2), (20004, 1, 8), (1000, 2, 3), (4, 1, 1)]:
+        L = PeerRegion(n, cl, world)
+        rows = cl * world
+        blocks = [("flags", L.off_flags, N_SLOTS * MAXW), ("cam0", L.off_cam, rows * 3), ("cam1", L.off_cam + L.cam_stride, rows * 3),
+                  ("g0", L.off_g, rows * L.row), ("g1", L.off_g + L.g_stride, rows * L.row),
+                  ("stage", L.off_stage, world * L.per4 * 4), ("y", L.off_y, world * L.per4 * 4)]
+        end = 0
+        for name, off, size in blocks:
+            assert off % 64 == 0, f"{name} not 256-byte aligned"
+            assert off >= end, f"{name} overlaps the previous block"
+            end = off + size
+        assert end <= L.words
+        assert L.row == 3 * n and L.n4 * 4 >= n * GEOM_FLOATS > (L.n4 - 1) * 4
+        assert world * L.per4 >= L.n4 > (world - 1) * L.per4 - world          # every float4 has exactly one owner shard
+        assert (L.row * 1) % 4 == 0 or n % 4                                   # rows are float4-addressable when N % 4 == 0
+
+
+def test_hit_mask_switch(monkeypatch):
+    """raster.new_hit_mask: one byte per sorted intersection, ADB_BLEND_HITS=0 turns the shared culling off."""
+    from artdeco_b200 import raster as R
+    vals = torch.zeros(1000, dtype=torch.int32)
+    m = R.new_hit_mask(vals)
+    assert m.dtype == torch.uint8 and m.numel() == 1000
+    assert R.new_hit_mask(vals[:0]).numel() == 1
+    monkeypatch.setenv("ADB_BLEND_HITS", "0")
+    assert R.new_hit_mask(vals) is None
