@@ -301,6 +301,35 @@ def test_backward_from_the_forward_hit_mask_equals_backward_with_its_own_culling
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("graph", [True, False], ids=["per_view_graphs", "eager"])
+def test_multi_gpu_step_path_on_one_rank_matches_the_single_process_step(cuda, graph):
+    """multiview.MultiViewStep(world > 1) takes the multi-GPU route — one CUDA graph PER VIEW, per-view gathers, the split SH
+    backward, the geometry reduce — which is otherwise only exercised by bench.py --gpus N.  With no process group the exchange
+    degenerates to one rank, so the route can run on one GPU and must reproduce the single-graph step."""
+    from artdeco_b200.multiview import MultiViewStep
+    N, W, H = 20000, 480, 272
+    sc = synthetic.raster_scene(N, seed=8)
+    cams = [synthetic.camera(W, H, view=v) for v in (1.0, 3.0, 5.0, 7.0)]
+    Vs, Ks = torch.stack([c[0] for c in cams]).to(cuda), torch.stack([c[1] for c in cams]).to(cuda)
+    t = {k: sc[k].to(cuda) for k in KEYS}
+    g = torch.Generator().manual_seed(6)
+    vc, va = torch.randn(4, H, W, 4, generator=g).to(cuda), torch.randn(4, H, W, generator=g).to(cuda)
+    ref = MultiViewStep(t, Vs, Ks, W, H, world=1)
+    eng = MultiViewStep(t, Vs, Ks, W, H, world=2, graph=graph)
+    assert ref.exchange is None and eng.exchange is not None
+    for e in (ref, eng):
+        e.set_upstream(vc, va)
+    for step in range(2):                                   # second step = graph replay
+        a, b = ref.step(), eng.step()
+        torch.cuda.synchronize()
+        for k in ("v_means", "v_quats", "v_scales", "v_opac", "v_sh"):
+            assert rel_err(b[k], a[k]) < 2e-5, f"step {step}: {k}"
+    if graph:
+        assert len(eng.graph) == 4 and len(ref.graph) == 1
+    assert eng.check_overflow() == ref.check_overflow()
+
+
+@pytest.mark.gpu
 def test_intersect_capacity_mode_has_no_host_sync_and_flags_overflow(cuda):
     """capacity mode of the tile-bucketed intersection: identical keys/vals/offsets without reading the count back, the true
     count and an overflow flag stay on the device, and an undersized capacity is memory-safe and flagged."""
