@@ -225,6 +225,8 @@ class PeerExchange:
     def push_view(self, c: int, splats: torch.Tensor, v_splats: torch.Tensor, campos: torch.Tensor | None = None):
         """Local view c: mask the colour gradient (SH clamp) and write it into every rank's table.  ``campos [C_local,3]``
         with the first view of the step."""
+        if tuple(splats.shape) != (self.n, 12) or tuple(v_splats.shape) != (self.n, 12) or not 0 <= c < self.views_local:
+            raise ValueError(f"push_view: expected splats / v_splats of shape ({self.n}, 12) and 0 <= c < {self.views_local}")
         self._begin_view(campos)
         n = self.n
         self._push(c, lambda dst, off, cam, camp, camoff: _lib.call(

@@ -222,7 +222,8 @@ def blend_forward(W, H, N, splats, vals, offsets, legacy=False, out=None, hits=N
                   _lib.stream())
         return colors, alphas, last_ids, main_ids
     if hits is not None:
-        assert hits.dtype == torch.uint8 and hits.numel() >= vals.numel()
+        if hits.dtype != torch.uint8 or hits.numel() < vals.numel() or hits.device != splats.device:
+            raise ValueError("blend_forward: hits must be a uint8 tensor with one byte per intersection (new_hit_mask)")
         _lib.call("adb_raster_blend_fwd_hits", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
                   _lib.ptr(offsets), _lib.ptr(colors), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(hits), _lib.stream())
         return colors, alphas, last_ids
@@ -236,6 +237,8 @@ def blend_backward(W, H, N, splats, vals, offsets, alphas, last_ids, v_colors, v
     ``hits``: the mask ``blend_forward(hits=)`` filled for the SAME splats / vals / offsets."""
     v_splats = out if out is not None else torch.zeros(N, SPLAT_STRIDE, dtype=torch.float32, device=splats.device)
     if hits is not None and not legacy:
+        if hits.dtype != torch.uint8 or hits.numel() < vals.numel() or hits.device != splats.device:
+            raise ValueError("blend_backward: hits must be the uint8 mask blend_forward filled for these intersections")
         _lib.call("adb_raster_blend_bwd_hits", W, H, N, _lib.ptr(splats), _lib.ptr(vals) if vals.numel() else None,
                   _lib.ptr(offsets), _lib.ptr(alphas), _lib.ptr(last_ids), _lib.ptr(v_colors), _lib.ptr(v_alphas),
                   _lib.ptr(v_splats), _lib.ptr(hits), _lib.stream())
