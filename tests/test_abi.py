@@ -82,3 +82,36 @@ def test_header_is_plain_c_and_cpp(tmp_path):
         assert r.returncode == 0 and not r.stderr.strip(), r.stderr
     text = (inc / "artdeco_b200.h").read_text()
     assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S).lower() and "#include <cuda" not in text
+
+
+def test_round2_entry_points_refuse_bad_arguments_before_touching_the_device():
+    """Error behaviour of the boundary (status 1 + adb_last_error, no exception, no CUDA call): checked on CPU for the entry
+    points added in round 2 — the peer-memory exchange, the shared-culling blend pair, the split SH backward."""
+    from artdeco_b200 import _lib
+    import artdeco_b200  # noqa: F401  (registers every signature)
+    L = _lib.lib()
+
+    def refused(rc, needle):
+        msg = L.adb_last_error()
+        return rc == 1 and msg is not None and needle in msg.decode()
+
+    assert refused(L.adb_peer_signal(None, 2, 0, 0, 1, None), "adb_peer_signal")
+    assert refused(L.adb_peer_signal(None, 9, 0, 0, 1, None), "adb_peer_signal")            # more than 8 ranks
+    assert refused(L.adb_peer_wait(None, 2, 0, 1, 1, 1.0, None, None), "adb_peer_wait")
+    assert refused(L.adb_peer_scatter(16, 4, None, None, 2, 0, None), "adb_peer_scatter")
+    assert refused(L.adb_peer_reduce_bcast(16, 4, None, None, 2, 5, None), "adb_peer_reduce_bcast")  # rank >= world
+    assert refused(L.adb_peer_push_rgb(8, None, None, None, 2, 0, None, None, 0, None), "adb_peer_push_rgb")
+    assert refused(L.adb_peer_bcast(6, None, None, 2, 0, None, None, 0, None), "adb_peer_bcast")   # not a multiple of 4 floats
+    assert refused(L.adb_peer_alloc(0, None), "adb_peer_alloc")
+    assert refused(L.adb_peer_export(None, None), "adb_peer_export")
+    assert refused(L.adb_peer_import(None, None), "adb_peer_import")
+    assert refused(L.adb_raster_blend_fwd_hits(16, 16, 0, None, None, None, None, None, None, None, None), "null hit_mask")
+    assert refused(L.adb_raster_blend_bwd_hits(16, 16, 4, None, None, None, None, None, None, None, None, None, None),
+                   "null hit_mask")
+    assert refused(L.adb_raster_sh_expand_multi(4, 0, None, 3, None, None, None, None), "adb_raster_sh_expand_multi")
+    assert refused(L.adb_raster_sh_expand_multi(4, 1, None, 4, None, None, None, None), "adb_raster_sh_expand_multi")  # degree > 3
+    assert refused(L.adb_raster_sh_dir_bwd_multi(4, 1, None, None, 3, None, None, None, None, None, None),
+                   "adb_raster_sh_dir_bwd_multi")
+    # empty problems are accepted without a launch
+    assert L.adb_raster_sh_expand_multi(0, 1, None, 3, None, None, None, None) == 0
+    assert L.adb_peer_free(None) == 0 and L.adb_peer_close(None) == 0
